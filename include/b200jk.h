@@ -1,0 +1,85 @@
+/*
+ * b200jk.h — C ABI of libb200jk.so, the B200-native J/K Fock-matrix builder.
+ *
+ * Every entry point takes plain pointers and sizes (numpy-owned host buffers); the library owns all
+ * device memory, streams and NCCL communicators inside the opaque handle.  All functions return 0 on
+ * success and a non-zero code on failure (message via b200jk_last_error); nothing ever calls exit().
+ *
+ * What each entry point replaces in the reference (file:line under /root/reference):
+ *
+ *   b200jk_create            the libcint tables consumed by every integral call:
+ *                            Mole._atm/_bas/_env  pyscf/gto/mole.py:963-1085, slots :58-88
+ *   b200jk_set_screening     _VHFOpt.__init__/init_cvhf_direct   pyscf/scf/_vhf.py:151-206
+ *                            -> CVHFnr_int2e_q_cond              pyscf/lib/vhf/optimizer.c:408-454
+ *   b200jk_direct_jk         _vhf.direct -> nr_direct_drv        pyscf/scf/_vhf.py:370-429,505-604
+ *                            -> CVHFnr_direct_drv / CVHFdot_nrs8 pyscf/lib/vhf/nr_direct.c:361-489,183-231
+ *                            -> libcint int2e_sph                (call site nr_direct.c:73)
+ *                            -> nrs8_ji_s2kl / nrs8_li_s2kj      pyscf/lib/vhf/nr_direct_dot.c:1293,1435
+ *                            -> CVHFnr_dm_cond, CVHFnrs8_prescreen  optimizer.c:494-518,90-117
+ *                            -> lib.hermi_triu                   pyscf/lib/numpy_helper.py:499
+ *   b200jk_df_build          incore.cholesky_eri                 pyscf/df/incore.py:129-220
+ *                            -> GTOnr3c_drv / GTOint2c           pyscf/lib/gto/fill_nr_3c.c:196, fill_int2c.c:36
+ *   b200jk_df_jk             df_jk.get_jk                        pyscf/df/df_jk.py:280-413
+ *                            -> AO2MOnr_e2_drv + NPdgemm         pyscf/lib/ao2mo/nr_ao2mo.c:1240, np_helper/npdot.c:32
+ *   b200jk_get_stats         (no reference equivalent; logger.timer 'vj and vk' pyscf/scf/hf.py:2158)
+ *
+ * Conventions: all matrices are C-contiguous fp64 in the reference's spherical AO order;
+ *   J_kl = sum_ij (ij|kl) D_ji ,  K_il = sum_jk (ij|kl) D_jk      (pyscf/scf/hf.py:906-907)
+ * no factor 1/2, no sign.  omega: 0 full Coulomb, >0 erf(omega r12)/r12 (pyscf/gto/mole.py:2940-2951).
+ */
+#ifndef B200JK_H
+#define B200JK_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200jk_handle_s* b200jk_handle;
+
+typedef struct {
+    double ms_total;        /* wall time of the last J/K call inside the library (host clock) */
+    double ms_kernels;      /* CUDA-event time of the J/K kernels of the last call */
+    double ms_h2d, ms_d2h;  /* copies of the last call */
+    uint64_t quartets_computed;  /* shell quartets that passed screening in the last direct call */
+    uint64_t quartets_screened;  /* shell quartets rejected on device */
+    uint64_t kernel_launches;    /* kernels launched by the last call */
+    int32_t n_dev_shells, n_cart, n_sph, n_pairs;
+} b200jk_stats;
+
+/* Build a handle from libcint-layout tables (copied).  device: CUDA device ordinal. */
+int b200jk_create(b200jk_handle* out, const int32_t* atm, int natm, const int32_t* bas, int nbas, const double* env,
+                  int nenv, int device);
+int b200jk_destroy(b200jk_handle h);
+
+/* Schwarz bounds on device + screened, sorted shell-pair lists.  Must precede b200jk_direct_jk. */
+int b200jk_set_screening(b200jk_handle h, double direct_scf_tol, double omega);
+
+/* dm: [n_dm, nao, nao]; hermi: 0 general real, 1 symmetric, 2 antisymmetric (hf.py:896-901).
+ * vj / vk: [n_dm, nao, nao] outputs, either may be NULL (with_j / with_k false). */
+int b200jk_direct_jk(b200jk_handle h, const double* dm, int n_dm, int nao, int hermi, double* vj, double* vk);
+
+/* Same computation with dm and outputs already resident on the device of the handle
+ * (device pointers); no host<->device copies.  Used by bench.py for the HBM-resident number. */
+int b200jk_direct_jk_device(b200jk_handle h, const double* dm_dev, int n_dm, int nao, int hermi, double* vj_dev,
+                            double* vk_dev);
+
+/* Density fitting: aux tables are a second libcint-layout set for the auxiliary basis. */
+int b200jk_df_build(b200jk_handle h, const int32_t* aux_atm, int aux_natm, const int32_t* aux_bas, int aux_nbas,
+                    const double* aux_env, int aux_nenv, double omega, double lindep);
+/* occ_coeff: [n_dm, nao, nocc] = C_occ*sqrt(occ) (may be NULL -> general-dm K algorithm). */
+int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao, const double* occ_coeff, int nocc, int hermi,
+                 double* vj, double* vk);
+int b200jk_df_naux(b200jk_handle h, int* naux);
+
+/* Schwarz table q_cond[nbas,nbas] in the reference's (contracted, spherical-order) shell indexing. */
+int b200jk_get_q_cond(b200jk_handle h, double* q_cond, int nbas);
+
+int b200jk_get_stats(b200jk_handle h, b200jk_stats* out);
+const char* b200jk_last_error(b200jk_handle h);
+const char* b200jk_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

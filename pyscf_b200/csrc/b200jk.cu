@@ -1,0 +1,640 @@
+// b200jk.cu — host side of libb200jk.so (C ABI in include/b200jk.h) and the kernel entry points.
+// With -DB200JK_EMULATE the same file builds with g++ into a CPU SIMT emulation used ONLY by
+// tests/ to exercise the host logic and kernel arithmetic without a GPU; the product library is
+// always the nvcc build and never falls back to the CPU.
+#include "../../include/b200jk.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "jk_block.cuh"
+#include "jk_classes.cuh"
+
+using namespace b200jk;
+
+extern "C" const unsigned char b200jk_rys_blob[];
+extern "C" const unsigned int b200jk_rys_blob_size;
+
+// ------------------------------------------------------------------------------------------------
+// backend: CUDA runtime or CPU emulation
+#ifndef B200JK_EMULATE
+#include <cuda_runtime.h>
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            char buf_[512];                                                                            \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            throw std::runtime_error(buf_);                                                            \
+        }                                                                                              \
+    } while (0)
+static void* dev_alloc(size_t n) { void* p = nullptr; CK(cudaMalloc(&p, n ? n : 8)); return p; }
+static void dev_free(void* p) { if (p) cudaFree(p); }
+static void h2d(void* d, const void* h, size_t n, cudaStream_t s = 0) { CK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); }
+static void d2h(void* h, const void* d, size_t n, cudaStream_t s = 0) { CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); }
+static void dev_zero(void* d, size_t n, cudaStream_t s = 0) { CK(cudaMemsetAsync(d, 0, n, s)); }
+static void dev_sync() { CK(cudaDeviceSynchronize()); }
+template <class F>
+__global__ void generic_kernel(long n, F f)
+{
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n) f(i);
+}
+template <class F>
+static void launch_1d(long n, const F& f, cudaStream_t s = 0)
+{
+    if (n <= 0) return;
+    generic_kernel<F><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(n, f);
+    CK(cudaGetLastError());
+}
+typedef cudaStream_t stream_t;
+#else
+#include <stdexcept>
+static void* dev_alloc(size_t n) { return calloc(1, n ? n : 8); }
+static void dev_free(void* p) { free(p); }
+typedef int stream_t;
+static void h2d(void* d, const void* h, size_t n, stream_t = 0) { memcpy(d, h, n); }
+static void d2h(void* h, const void* d, size_t n, stream_t = 0) { memcpy(h, d, n); }
+static void dev_zero(void* d, size_t n, stream_t = 0) { memset(d, 0, n); }
+static void dev_sync() {}
+template <class F>
+static void launch_1d(long n, const F& f, stream_t = 0)
+{
+    for (long i = 0; i < n; i++) f(i);
+}
+#endif
+#include <stdexcept>
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int ATM_SLOTS = 6, BAS_SLOTS = 8, ATOM_OF = 0, ANG_OF = 1, NPRIM_OF = 2, NCTR_OF = 3, PTR_EXP = 5, PTR_COEFF = 6,
+              PTR_COORD = 1;
+constexpr int LAO_MAX = 3;                                 // orbital shells up to f on the 4-center path
+constexpr int NPC = (LAO_MAX + 1) * (LAO_MAX + 2) / 2;     // pair classes
+constexpr double PRIM_CUT = 1e-18;                         // drop primitive pairs with |cc| below this
+
+struct DevShell {
+    int l, nprim, ref_shell, sph_off, cart_off;
+    double r[3];
+    std::vector<double> e, c;
+};
+
+struct PairClass {
+    int la = 0, lb = 0;
+    std::vector<ShellPair> all;      // every pair, unsorted, q not set
+    std::vector<ShellPair> kept;     // screened + sorted by q descending
+    ShellPair* d_all = nullptr;
+    ShellPair* d_kept = nullptr;
+};
+
+double binom(int n, int k)
+{
+    if (k < 0 || k > n) return 0.0;
+    double r = 1.0;
+    for (int i = 1; i <= k; i++) r = r * (n - k + i) / i;
+    return r;
+}
+double fact(int n) { double r = 1; for (int i = 2; i <= n; i++) r *= i; return r; }
+int cart_index(int l, int lx, int ly)
+{
+    int idx = 0;
+    for (int x = l; x > lx; x--) idx += l - x + 1;
+    return idx + (l - lx - ly);
+}
+// Real solid harmonics (orthonormal on the sphere) in terms of Cartesian monomials, libcint order
+// (p: x,y,z ; l>=2: m=-l..l).  Helgaker, Jorgensen, Olsen, "Molecular Electronic-Structure Theory", eq. 6.4.47.
+std::vector<double> make_c2s(int l)
+{
+    int nc = ncart(l), ns = 2 * l + 1;
+    std::vector<double> T((size_t)ns * nc, 0.0);
+    if (l == 0) { T[0] = 0.282094791773878143; return T; }
+    if (l == 1) { for (int i = 0; i < 3; i++) T[i * 3 + i] = 0.488602511902919921; return T; }
+    double ang = std::sqrt((2 * l + 1) / (4.0 * M_PI));
+    for (int m = -l; m <= l; m++) {
+        int am = std::abs(m);
+        double N = 1.0 / (std::pow(2.0, am) * fact(l)) * std::sqrt(2.0 * fact(l + am) * fact(l - am) / (m == 0 ? 2.0 : 1.0));
+        int two_vm = (m < 0) ? 1 : 0;
+        for (int t = 0; t <= (l - am) / 2; t++)
+            for (int u = 0; u <= t; u++) {
+                int vmax2 = 2 * (int)std::floor(am / 2.0 - two_vm / 2.0) + two_vm;
+                for (int two_v = two_vm; two_v <= vmax2; two_v += 2) {
+                    int sp = t + (two_v - two_vm) / 2;
+                    double Cf = ((sp & 1) ? -1.0 : 1.0) * std::pow(0.25, t) * binom(l, t) * binom(l - t, am + t) *
+                                binom(t, u) * binom(am, two_v);
+                    int lx = 2 * t + am - 2 * u - two_v, ly = 2 * u + two_v, lz = l - 2 * t - am;
+                    if (lx < 0 || ly < 0 || lz < 0) continue;
+                    T[(size_t)(m + l) * nc + cart_index(l, lx, ly)] += ang * N * Cf;
+                }
+            }
+    }
+    return T;
+}
+
+}  // namespace
+
+struct b200jk_handle_s {
+    int device = 0;
+    std::string err;
+    std::vector<DevShell> sh;
+    int nsh = 0, ncart = 0, nsph = 0, nbas_ref = 0;
+    std::vector<PrimPair> prims;
+    PrimPair* d_prims = nullptr;
+    PairClass pc[NPC];
+    double* d_rys = nullptr;
+    RysTables tb{nullptr, nullptr};
+    // AO transform tables
+    int *d_cart_sh = nullptr, *d_cart_comp = nullptr, *d_sph_sh = nullptr, *d_sph_m = nullptr;
+    int *d_sh_l = nullptr, *d_sh_cart = nullptr, *d_sh_sph = nullptr;
+    double* d_c2s = nullptr;
+    int c2s_off[LMAX + 2] = {0};
+    int* d_c2s_off = nullptr;
+    std::vector<int> ref_shell_of;  // device shell -> reference shell
+    double tol = 1e-13, omega = 0.0;
+    bool screened = false;
+    // workspaces
+    size_t ws_ndm = 0;
+    double *d_dm_sph = nullptr, *d_out_sph = nullptr, *d_dmj = nullptr, *d_dmk = nullptr, *d_vj = nullptr, *d_vk = nullptr,
+           *d_dmc = nullptr;
+    unsigned long long* d_counters = nullptr;
+    b200jk_stats stats{};
+#ifndef B200JK_EMULATE
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+#endif
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// small kernels (functors so that the same code runs under emulation)
+struct SchwarzFn {
+    ShellPair* pairs; const PrimPair* prims; RysTables tb; double omega; int la, lb;
+    B2_HD void operator()(long i) const { pairs[i].q = schwarz_pair(la, lb, pairs[i], prims, tb, omega); }
+};
+
+// D_cart[s][mu][nu] = sum_{m,m'} T[m,mu] Dsym[m,m'] T[m',nu]; mode 0: (D+D^T)/2, 1: (D-D^T)/2, 2: D as is
+struct Sph2CartFn {
+    const double* dsph; double* dcart; int nsph, ncart, mode;
+    const int *cart_sh, *cart_comp, *sh_l, *sh_sph, *c2s_off; const double* c2s;
+    B2_HD void operator()(long idx) const
+    {
+        long n2 = (long)ncart * ncart;
+        int s = (int)(idx / n2);
+        long rem = idx - s * n2;
+        int mu = (int)(rem / ncart), nu = (int)(rem - (long)mu * ncart);
+        int sa = cart_sh[mu], sb = cart_sh[nu];
+        int la = sh_l[sa], lb = sh_l[sb];
+        int nca = ncart_rt(la), ncb = ncart_rt(lb);
+        const double* Ta = c2s + c2s_off[la] + cart_comp[mu];
+        const double* Tb = c2s + c2s_off[lb] + cart_comp[nu];
+        const double* D = dsph + (size_t)s * nsph * nsph;
+        int oa = sh_sph[sa], ob = sh_sph[sb];
+        double acc = 0.0;
+        for (int m = 0; m < 2 * la + 1; m++) {
+            double ta = Ta[m * nca];
+            if (ta == 0.0) continue;
+            for (int mp = 0; mp < 2 * lb + 1; mp++) {
+                double tb_ = Tb[mp * ncb];
+                if (tb_ == 0.0) continue;
+                double d1 = D[(size_t)(oa + m) * nsph + ob + mp], d2 = D[(size_t)(ob + mp) * nsph + oa + m];
+                double d = (mode == 0) ? 0.5 * (d1 + d2) : (mode == 1 ? 0.5 * (d1 - d2) : d1);
+                acc += ta * tb_ * d;
+            }
+        }
+        dcart[idx] = acc;
+    }
+    static B2_HD int ncart_rt(int l) { return (l + 1) * (l + 2) / 2; }
+};
+
+// out_sph[s][m][m'] (+)= sum T[m,mu] (X[mu,nu] + sign*X[nu,mu]) T[m',nu]
+struct Cart2SphFn {
+    const double* xcart; double* osph; int nsph, ncart; double sign; int accumulate;
+    const int *sph_sh, *sph_m, *sh_l, *sh_cart, *c2s_off; const double* c2s;
+    B2_HD void operator()(long idx) const
+    {
+        long n2 = (long)nsph * nsph;
+        int s = (int)(idx / n2);
+        long rem = idx - s * n2;
+        int a = (int)(rem / nsph), b = (int)(rem - (long)a * nsph);
+        int sa = sph_sh[a], sb = sph_sh[b];
+        int la = sh_l[sa], lb = sh_l[sb];
+        int nca = (la + 1) * (la + 2) / 2, ncb = (lb + 1) * (lb + 2) / 2;
+        const double* Ta = c2s + c2s_off[la] + sph_m[a] * nca;
+        const double* Tb = c2s + c2s_off[lb] + sph_m[b] * ncb;
+        const double* X = xcart + (size_t)s * ncart * ncart;
+        int oa = sh_cart[sa], ob = sh_cart[sb];
+        double acc = 0.0;
+        for (int c = 0; c < nca; c++) {
+            double ta = Ta[c];
+            if (ta == 0.0) continue;
+            for (int d = 0; d < ncb; d++) {
+                double tb_ = Tb[d];
+                if (tb_ == 0.0) continue;
+                acc += ta * tb_ * (X[(size_t)(oa + c) * ncart + ob + d] + sign * X[(size_t)(ob + d) * ncart + oa + c]);
+            }
+        }
+        if (accumulate) osph[idx] += acc; else osph[idx] = acc;
+    }
+};
+
+// dm_cond over device shells: max |D_cart| over the block and over all density matrices
+struct DmCondFn {
+    const double* dj; int ndj; const double* dk; int ndk; double* dmc; int nsh, ncart; const int *sh_l, *sh_cart;
+    B2_HD void operator()(long idx) const
+    {
+        int i = (int)(idx / nsh), j = (int)(idx - (long)i * nsh);
+        int ni = (sh_l[i] + 1) * (sh_l[i] + 2) / 2, nj = (sh_l[j] + 1) * (sh_l[j] + 2) / 2;
+        double m = 0.0;
+        for (int pass = 0; pass < 2; pass++) {
+            const double* D = pass ? dk : dj;
+            int nd = pass ? ndk : ndj;
+            if (!D) continue;
+            for (int s = 0; s < nd; s++)
+                for (int a = 0; a < ni; a++)
+                    for (int b = 0; b < nj; b++) {
+                        double v = fabs(D[(size_t)s * ncart * ncart + (size_t)(sh_cart[i] + a) * ncart + sh_cart[j] + b]);
+                        m = v > m ? v : m;
+                    }
+        }
+        dmc[idx] = m;
+    }
+};
+
+int pair_class_id(int la, int lb) { return la * (la + 1) / 2 + lb; }
+
+void set_err(b200jk_handle h, const std::string& m) { if (h) h->err = m; }
+
+template <class T>
+T* upload(const std::vector<T>& v)
+{
+    T* d = (T*)dev_alloc(v.size() * sizeof(T));
+    if (!v.empty()) h2d(d, v.data(), v.size() * sizeof(T));
+    return d;
+}
+
+void ensure_workspace(b200jk_handle h, int n_dm)
+{
+    if ((size_t)n_dm <= h->ws_ndm) return;
+    for (double** p : {&h->d_dm_sph, &h->d_out_sph, &h->d_dmj, &h->d_dmk, &h->d_vj, &h->d_vk}) { dev_free(*p); *p = nullptr; }
+    size_t ns2 = (size_t)h->nsph * h->nsph, nc2 = (size_t)h->ncart * h->ncart;
+    h->d_dm_sph = (double*)dev_alloc(ns2 * n_dm * 8);
+    h->d_out_sph = (double*)dev_alloc(ns2 * n_dm * 8 * 2);
+    h->d_dmj = (double*)dev_alloc(nc2 * n_dm * 8);
+    h->d_dmk = (double*)dev_alloc(nc2 * n_dm * 8 * 2);
+    h->d_vj = (double*)dev_alloc(nc2 * n_dm * 8);
+    h->d_vk = (double*)dev_alloc(nc2 * n_dm * 8 * 2);
+    h->ws_ndm = n_dm;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* b200jk_version(void)
+{
+#ifdef B200JK_EMULATE
+    return "b200jk 0.1 (CPU SIMT emulation — tests only)";
+#else
+    return "b200jk 0.1 (sm_100a)";
+#endif
+}
+
+extern "C" const char* b200jk_last_error(b200jk_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" int b200jk_create(b200jk_handle* out, const int32_t* atm, int natm, const int32_t* bas, int nbas,
+                             const double* env, int nenv, int device)
+{
+    if (!out) return 1;
+    *out = nullptr;
+    b200jk_handle h = new b200jk_handle_s();
+    try {
+        h->device = device;
+#ifndef B200JK_EMULATE
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            throw std::runtime_error("no CUDA device: libb200jk has no CPU fallback");
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreate(&h->stream));
+        CK(cudaEventCreate(&h->ev0));
+        CK(cudaEventCreate(&h->ev1));
+#endif
+        (void)natm; (void)nenv;
+        // ---- device shells: general contractions are split into segmented shells
+        std::vector<DevShell> tmp;
+        int sph = 0;
+        for (int ib = 0; ib < nbas; ib++) {
+            const int32_t* b = bas + ib * BAS_SLOTS;
+            int l = b[ANG_OF], np = b[NPRIM_OF], nc = b[NCTR_OF];
+            if (l > LAO_MAX) throw std::runtime_error("angular momentum > f is not supported on the 4-center path");
+            const double* r = env + atm[b[ATOM_OF] * ATM_SLOTS + PTR_COORD];
+            for (int c = 0; c < nc; c++) {
+                DevShell s;
+                s.l = l; s.ref_shell = ib; s.sph_off = sph + c * (2 * l + 1); s.cart_off = 0;
+                s.r[0] = r[0]; s.r[1] = r[1]; s.r[2] = r[2];
+                for (int p = 0; p < np; p++) {
+                    double cf = env[b[PTR_COEFF] + c * np + p];
+                    if (cf != 0.0) { s.e.push_back(env[b[PTR_EXP] + p]); s.c.push_back(cf); }
+                }
+                s.nprim = (int)s.e.size();
+                tmp.push_back(s);
+            }
+            sph += nc * (2 * l + 1);
+        }
+        h->nsph = sph;
+        h->nbas_ref = nbas;
+        std::stable_sort(tmp.begin(), tmp.end(), [](const DevShell& a, const DevShell& b) { return a.l < b.l; });
+        int co = 0;
+        for (auto& s : tmp) { s.cart_off = co; co += ncart(s.l); }
+        h->ncart = co;
+        h->sh = tmp;
+        h->nsh = (int)tmp.size();
+
+        // ---- AO transform tables
+        std::vector<int> cart_sh(h->ncart), cart_comp(h->ncart), sph_sh(h->nsph), sph_m(h->nsph), sh_l(h->nsh), sh_cart(h->nsh),
+            sh_sph(h->nsh);
+        for (int i = 0; i < h->nsh; i++) {
+            const DevShell& s = h->sh[i];
+            sh_l[i] = s.l; sh_cart[i] = s.cart_off; sh_sph[i] = s.sph_off;
+            for (int a = 0; a < ncart(s.l); a++) { cart_sh[s.cart_off + a] = i; cart_comp[s.cart_off + a] = a; }
+            for (int m = 0; m < 2 * s.l + 1; m++) { sph_sh[s.sph_off + m] = i; sph_m[s.sph_off + m] = m; }
+            h->ref_shell_of.push_back(s.ref_shell);
+        }
+        std::vector<double> c2s;
+        std::vector<int> c2s_off;
+        for (int l = 0; l <= LMAX; l++) {
+            c2s_off.push_back((int)c2s.size());
+            auto T = make_c2s(l);
+            c2s.insert(c2s.end(), T.begin(), T.end());
+        }
+        h->d_cart_sh = upload(cart_sh); h->d_cart_comp = upload(cart_comp);
+        h->d_sph_sh = upload(sph_sh); h->d_sph_m = upload(sph_m);
+        h->d_sh_l = upload(sh_l); h->d_sh_cart = upload(sh_cart); h->d_sh_sph = upload(sh_sph);
+        h->d_c2s = upload(c2s); h->d_c2s_off = upload(c2s_off);
+
+        // ---- Rys tables
+        {
+            const double* blob = (const double*)b200jk_rys_blob;
+            size_t nd = b200jk_rys_blob_size / 8;
+            if ((int)blob[0] != RYS_NMAX || (int)blob[1] != RYS_DEG || (int)blob[2] != RYS_NINT)
+                throw std::runtime_error("rys table header mismatch");
+            h->d_rys = (double*)dev_alloc(nd * 8);
+            h2d(h->d_rys, blob, nd * 8);
+            h->tb.herm = h->d_rys + 5;
+            h->tb.cheb = h->d_rys + 5 + RYS_NMAX * (RYS_NMAX + 1);
+        }
+
+        // ---- shell pairs and primitive pairs per class
+        for (int la = 0; la <= LAO_MAX; la++)
+            for (int lb = 0; lb <= la; lb++) { h->pc[pair_class_id(la, lb)].la = la; h->pc[pair_class_id(la, lb)].lb = lb; }
+        for (int i = 0; i < h->nsh; i++)
+            for (int j = 0; j <= i; j++) {
+                const DevShell &a = h->sh[i], &b = h->sh[j];  // sorted by l => a.l >= b.l
+                PairClass& P = h->pc[pair_class_id(a.l, b.l)];
+                ShellPair sp{};
+                sp.ABx = a.r[0] - b.r[0]; sp.ABy = a.r[1] - b.r[1]; sp.ABz = a.r[2] - b.r[2];
+                double r2 = sp.ABx * sp.ABx + sp.ABy * sp.ABy + sp.ABz * sp.ABz;
+                sp.ish = i; sp.jsh = j; sp.i0 = a.cart_off; sp.j0 = b.cart_off; sp.same = (i == j);
+                sp.prim_off = (int)h->prims.size();
+                int np = 0;
+                for (int pa = 0; pa < a.nprim; pa++)
+                    for (int pb = 0; pb < b.nprim; pb++) {
+                        double ea = a.e[pa], eb = b.e[pb], p = ea + eb;
+                        double cc = a.c[pa] * b.c[pb] * std::exp(-ea * eb / p * r2);
+                        if (std::fabs(cc) < PRIM_CUT) continue;
+                        PrimPair pp;
+                        pp.p = p;
+                        pp.Px = (ea * a.r[0] + eb * b.r[0]) / p; pp.Py = (ea * a.r[1] + eb * b.r[1]) / p; pp.Pz = (ea * a.r[2] + eb * b.r[2]) / p;
+                        pp.PAx = pp.Px - a.r[0]; pp.PAy = pp.Py - a.r[1]; pp.PAz = pp.Pz - a.r[2];
+                        pp.cc = cc;
+                        h->prims.push_back(pp);
+                        np++;
+                    }
+                sp.nprim = np;
+                sp.q = 0.0;
+                if (np > 0) P.all.push_back(sp);
+            }
+        h->d_prims = upload(h->prims);
+        int npairs = 0;
+        for (int c = 0; c < NPC; c++) { h->pc[c].d_all = upload(h->pc[c].all); npairs += (int)h->pc[c].all.size(); }
+        h->d_dmc = (double*)dev_alloc((size_t)h->nsh * h->nsh * 8);
+        h->d_counters = (unsigned long long*)dev_alloc(16);
+        h->stats.n_dev_shells = h->nsh; h->stats.n_cart = h->ncart; h->stats.n_sph = h->nsph; h->stats.n_pairs = npairs;
+        dev_sync();
+    } catch (std::exception& e) {
+        // keep the handle so the caller can read the message
+        h->err = e.what();
+        *out = h;
+        return 2;
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" int b200jk_destroy(b200jk_handle h)
+{
+    if (!h) return 0;
+    dev_free(h->d_prims); dev_free(h->d_rys);
+    for (int c = 0; c < NPC; c++) { dev_free(h->pc[c].d_all); dev_free(h->pc[c].d_kept); }
+    dev_free(h->d_cart_sh); dev_free(h->d_cart_comp); dev_free(h->d_sph_sh); dev_free(h->d_sph_m);
+    dev_free(h->d_sh_l); dev_free(h->d_sh_cart); dev_free(h->d_sh_sph); dev_free(h->d_c2s); dev_free(h->d_c2s_off);
+    dev_free(h->d_dm_sph); dev_free(h->d_out_sph); dev_free(h->d_dmj); dev_free(h->d_dmk); dev_free(h->d_vj); dev_free(h->d_vk);
+    dev_free(h->d_dmc); dev_free(h->d_counters);
+#ifndef B200JK_EMULATE
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+#endif
+    delete h;
+    return 0;
+}
+
+extern "C" int b200jk_set_screening(b200jk_handle h, double tol, double omega)
+{
+    if (!h) return 1;
+    try {
+        if (omega < 0.0) throw std::runtime_error("short-range (omega<0) operator is not implemented on the device path");
+        h->tol = tol; h->omega = omega;
+        double qmax = 0.0;
+        for (int c = 0; c < NPC; c++) {
+            PairClass& P = h->pc[c];
+            if (P.all.empty()) continue;
+            SchwarzFn fn{P.d_all, h->d_prims, h->tb, omega, P.la, P.lb};
+            launch_1d((long)P.all.size(), fn);
+        }
+        dev_sync();
+        for (int c = 0; c < NPC; c++) {
+            PairClass& P = h->pc[c];
+            if (P.all.empty()) continue;
+            d2h(P.all.data(), P.d_all, P.all.size() * sizeof(ShellPair));
+        }
+        dev_sync();
+        for (int c = 0; c < NPC; c++)
+            for (auto& sp : h->pc[c].all) qmax = std::max(qmax, sp.q);
+        for (int c = 0; c < NPC; c++) {
+            PairClass& P = h->pc[c];
+            P.kept.clear();
+            // a pair can only survive q_ij*q_kl > tol if q_ij*qmax > tol (density factors <= O(1) are
+            // applied per quartet on device; keep the Schwarz-only bound here, like q_cond in the reference)
+            for (auto& sp : P.all)
+                if (sp.q * qmax > tol * 1e-2) P.kept.push_back(sp);
+            std::stable_sort(P.kept.begin(), P.kept.end(), [](const ShellPair& a, const ShellPair& b) { return a.q > b.q; });
+            dev_free(P.d_kept);
+            P.d_kept = upload(P.kept);
+        }
+        dev_sync();
+        h->screened = true;
+    } catch (std::exception& e) { set_err(h, e.what()); return 2; }
+    return 0;
+}
+
+extern "C" int b200jk_get_q_cond(b200jk_handle h, double* q, int nbas)
+{
+    if (!h || !h->screened) { set_err(h, "call b200jk_set_screening first"); return 1; }
+    if (nbas != h->nbas_ref) { set_err(h, "nbas mismatch"); return 1; }
+    for (long i = 0; i < (long)nbas * nbas; i++) q[i] = 1e-100;
+    for (int c = 0; c < NPC; c++)
+        for (auto& sp : h->pc[c].all) {
+            int I = h->ref_shell_of[sp.ish], J = h->ref_shell_of[sp.jsh];
+            double v = std::max(sp.q, 1e-100);
+            q[(long)I * nbas + J] = std::max(q[(long)I * nbas + J], v);
+            q[(long)J * nbas + I] = std::max(q[(long)J * nbas + I], v);
+        }
+    return 0;
+}
+
+static int direct_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, int hermi, double* vj, double* vk,
+                          bool on_device)
+{
+    if (!h) return 1;
+    try {
+        if (!h->screened) throw std::runtime_error("call b200jk_set_screening before b200jk_direct_jk");
+        if (nao != h->nsph) throw std::runtime_error("nao does not match the basis of this handle");
+        if (n_dm < 1) throw std::runtime_error("n_dm < 1");
+        if (!vj && !vk) return 0;
+        auto t0 = std::chrono::steady_clock::now();
+        ensure_workspace(h, n_dm);
+        size_t ns2 = (size_t)h->nsph * h->nsph, nc2 = (size_t)h->ncart * h->ncart;
+#ifndef B200JK_EMULATE
+        CK(cudaSetDevice(h->device));
+        stream_t st = h->stream;
+#else
+        stream_t st = 0;
+#endif
+        const double* dsph = dm;
+        if (!on_device) { h2d(h->d_dm_sph, dm, ns2 * n_dm * 8, st); dsph = h->d_dm_sph; }
+        uint64_t launches = 0;
+        // ---- densities in the Cartesian device basis: J sees the symmetric part; K sees sym (and antisym if hermi != 1)
+        Sph2CartFn s2c{dsph, h->d_dmj, h->nsph, h->ncart, 0, h->d_cart_sh, h->d_cart_comp, h->d_sh_l, h->d_sh_sph, h->d_c2s_off, h->d_c2s};
+        int n_dm_k = n_dm;
+        const double* dmk = h->d_dmj;
+        bool need_sym = (hermi != 2), need_anti = (hermi != 1);
+        if (vj || (vk && need_sym)) { launch_1d((long)nc2 * n_dm, s2c, st); launches++; }
+        if (vk && need_anti) {
+            Sph2CartFn a2c = s2c; a2c.mode = 1;
+            if (need_sym) { a2c.dcart = h->d_dmk + nc2 * n_dm; }
+            else { a2c.dcart = h->d_dmk; }
+            launch_1d((long)nc2 * n_dm, a2c, st); launches++;
+            if (need_sym) {
+                // [sym ; anti] contiguous in d_dmk
+#ifndef B200JK_EMULATE
+                CK(cudaMemcpyAsync(h->d_dmk, h->d_dmj, nc2 * n_dm * 8, cudaMemcpyDeviceToDevice, st));
+#else
+                memcpy(h->d_dmk, h->d_dmj, nc2 * n_dm * 8);
+#endif
+                n_dm_k = 2 * n_dm;
+            }
+            dmk = h->d_dmk;
+        }
+        DmCondFn dc{vj ? h->d_dmj : nullptr, n_dm, vk ? dmk : nullptr, n_dm_k, h->d_dmc, h->nsh, h->ncart, h->d_sh_l, h->d_sh_cart};
+        launch_1d((long)h->nsh * h->nsh, dc, st); launches++;
+        if (vj) dev_zero(h->d_vj, nc2 * n_dm * 8, st);
+        if (vk) dev_zero(h->d_vk, nc2 * n_dm_k * 8, st);
+        dev_zero(h->d_counters, 16, st);
+
+        KParams P{};
+        P.prims = h->d_prims; P.tb = h->tb; P.omega = h->omega; P.tol = h->tol;
+        P.dmc = h->d_dmc; P.nsh = h->nsh;
+        P.dmj = h->d_dmj; P.dmk = dmk; P.vj = vj ? h->d_vj : nullptr; P.vk = vk ? h->d_vk : nullptr;
+        P.n = h->ncart; P.n_dm_j = n_dm; P.n_dm_k = n_dm_k;
+        P.counters = h->d_counters;
+#ifndef B200JK_EMULATE
+        CK(cudaEventRecord(h->ev0, st));
+#endif
+        for (int cb = NPC - 1; cb >= 0; cb--)
+            for (int ck = cb; ck >= 0; ck--) {
+                PairClass &B = h->pc[cb], &K = h->pc[ck];
+                if (B.kept.empty() || K.kept.empty()) continue;
+                P.bra_pairs = B.d_kept; P.nbra = (int)B.kept.size();
+                P.ket_pairs = K.d_kept; P.nket = (int)K.kept.size();
+                P.same_class = (cb == ck);
+                launch_class(cb, ck, P, st);
+                launches++;
+            }
+#ifndef B200JK_EMULATE
+        CK(cudaEventRecord(h->ev1, st));
+#endif
+        // ---- back to the spherical basis with the final symmetrisation
+        Cart2SphFn c2s{nullptr, nullptr, h->nsph, h->ncart, 1.0, 0, h->d_sph_sh, h->d_sph_m, h->d_sh_l, h->d_sh_cart, h->d_c2s_off, h->d_c2s};
+        double* oj = on_device ? vj : h->d_out_sph;
+        double* ok = on_device ? vk : h->d_out_sph + ns2 * n_dm;
+        if (vj) { c2s.xcart = h->d_vj; c2s.osph = oj; c2s.sign = 1.0; c2s.accumulate = 0; launch_1d((long)ns2 * n_dm, c2s, st); launches++; }
+        if (vk) {
+            c2s.osph = ok;
+            if (need_sym) { c2s.xcart = h->d_vk; c2s.sign = 1.0; c2s.accumulate = 0; launch_1d((long)ns2 * n_dm, c2s, st); launches++; }
+            if (need_anti) {
+                c2s.xcart = h->d_vk + (need_sym ? nc2 * n_dm : 0); c2s.sign = -1.0; c2s.accumulate = need_sym ? 1 : 0;
+                launch_1d((long)ns2 * n_dm, c2s, st); launches++;
+            }
+        }
+        if (!on_device) {
+            if (vj) d2h(vj, oj, ns2 * n_dm * 8, st);
+            if (vk) d2h(vk, ok, ns2 * n_dm * 8, st);
+        }
+        unsigned long long cnt[2] = {0, 0};
+        d2h(cnt, h->d_counters, 16, st);
+#ifndef B200JK_EMULATE
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->stats.ms_kernels = ms;
+#endif
+        auto t1 = std::chrono::steady_clock::now();
+        h->stats.ms_total = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        h->stats.quartets_computed = cnt[0];
+        h->stats.quartets_screened = cnt[1];
+        h->stats.kernel_launches = launches;
+    } catch (std::exception& e) { set_err(h, e.what()); return 2; }
+    return 0;
+}
+
+extern "C" int b200jk_direct_jk(b200jk_handle h, const double* dm, int n_dm, int nao, int hermi, double* vj, double* vk)
+{
+    return direct_jk_impl(h, dm, n_dm, nao, hermi, vj, vk, false);
+}
+extern "C" int b200jk_direct_jk_device(b200jk_handle h, const double* dm, int n_dm, int nao, int hermi, double* vj, double* vk)
+{
+    return direct_jk_impl(h, dm, n_dm, nao, hermi, vj, vk, true);
+}
+
+extern "C" int b200jk_get_stats(b200jk_handle h, b200jk_stats* out)
+{
+    if (!h || !out) return 1;
+    *out = h->stats;
+    return 0;
+}
+
+// ---- density fitting entry points live in df.cu; stubs until that translation unit is linked
+#ifndef B200JK_HAVE_DF
+extern "C" int b200jk_df_build(b200jk_handle h, const int32_t*, int, const int32_t*, int, const double*, int, double, double)
+{ set_err(h, "density-fitting path not built into this library"); return 3; }
+extern "C" int b200jk_df_jk(b200jk_handle h, const double*, int, int, const double*, int, int, double*, double*)
+{ set_err(h, "density-fitting path not built into this library"); return 3; }
+extern "C" int b200jk_df_naux(b200jk_handle h, int*)
+{ set_err(h, "density-fitting path not built into this library"); return 3; }
+#endif

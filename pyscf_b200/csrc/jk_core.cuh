@@ -1,0 +1,483 @@
+// jk_core.cuh — device-side arithmetic of the 4-center direct J/K path (sm_100a), written so that
+// the same templates also compile with g++ for the CPU SIMT-emulation tests (tests/emu).
+//
+// Replaces (reference file:line):
+//   libcint int2e_sph (Rys quadrature)       called at pyscf/lib/vhf/nr_direct.c:73
+//   nrs8_ji_s2kl / nrs8_li_s2kj digestion    pyscf/lib/vhf/nr_direct_dot.c:1293,1435
+//   CVHFnrs8_prescreen                       pyscf/lib/vhf/optimizer.c:90-117
+// Design: one kernel per angular-momentum class (LI LJ|LK LL).  A CTA owns one bra
+// shell pair (ij) and walks a screened list of ket pairs (kl), NQ at a time.  Inside a quartet the
+// ket Cartesian component pair (c,d) is the THREAD index and the bra component block (a,b) lives in
+// REGISTERS; the 2-D Rys integrals I(n,m) are produced cooperatively into shared memory and each
+// thread applies the horizontal recurrences for its own (c,d) in registers.  ERIs are never
+// stored: they are contracted with the density in registers and flushed as fp64 reductions.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define B2_HD __host__ __device__ __forceinline__
+#define B2_UNROLL _Pragma("unroll")
+#else
+#define B2_HD inline __attribute__((always_inline))
+#define B2_UNROLL
+#endif
+
+namespace b200jk {
+
+constexpr int LMAX = 4;  // g shells (aux); orbital classes are generated up to f
+constexpr int RYS_NMAX = 9, RYS_DEG = 13, RYS_NINT = 40;
+constexpr double RYS_H = 2.5, RYS_XMAX = 100.0;
+constexpr double PI_25_2 = 34.98683665524972497;  // 2*pi^(5/2)
+
+B2_HD constexpr int ncart(int l) { return (l + 1) * (l + 2) / 2; }
+
+// libcint Cartesian order: lx descending, then ly descending (pyscf/lib/parameters.py:69-77)
+B2_HD constexpr int cart_px(int l, int a)
+{
+    int n = 0;
+    for (int x = l; x >= 0; x--)
+        for (int y = l - x; y >= 0; y--) {
+            if (n == a) return x;
+            n++;
+        }
+    return 0;
+}
+B2_HD constexpr int cart_py(int l, int a)
+{
+    int n = 0;
+    for (int x = l; x >= 0; x--)
+        for (int y = l - x; y >= 0; y--) {
+            if (n == a) return y;
+            n++;
+        }
+    return 0;
+}
+B2_HD constexpr int cart_pz(int l, int a) { return l - cart_px(l, a) - cart_py(l, a); }
+
+// ---------------------------------------------------------------------------------------------
+// Rys roots and weights from the tables made by tools/gen_rys_tables.py
+struct RysTables {
+    const double* herm;  // for n: offset n(n-1): u_r*x (n values), w_r*sqrt(x) (n values)
+    const double* cheb;  // for n: offset NINT*28*n(n-1)/2: [NINT][n][2][14]
+};
+
+B2_HD void rys_root(const RysTables& tb, int n, int r, double x, double& u, double& w)
+{
+    if (x >= RYS_XMAX) {
+        const double* h = tb.herm + n * (n - 1);
+        double ix = 1.0 / x;
+        u = h[r] * ix;
+        w = h[n + r] * sqrt(ix);
+        return;
+    }
+    int iv = (int)(x * (1.0 / RYS_H));
+    if (iv > RYS_NINT - 1) iv = RYS_NINT - 1;
+    double t = (x - iv * RYS_H) * (2.0 / RYS_H) - 1.0;
+    const double* c = tb.cheb + (size_t)RYS_NINT * 28 * (n * (n - 1) / 2) + (size_t)(iv * n + r) * 28;
+    double t2 = 2.0 * t, b1 = 0.0, b2 = 0.0, d1 = 0.0, d2 = 0.0;
+    B2_UNROLL
+    for (int j = RYS_DEG; j >= 1; j--) {
+        double tb_ = t2 * b1 - b2 + c[j];
+        b2 = b1; b1 = tb_;
+        double td_ = t2 * d1 - d2 + c[14 + j];
+        d2 = d1; d1 = td_;
+    }
+    u = t * b1 - b2 + c[0];
+    w = t * d1 - d2 + c[14];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shell-pair data (HBM layout)
+struct PrimPair {  // 64 bytes, one per surviving primitive pair
+    double p;             // a_i + a_j
+    double Px, Py, Pz;    // Gaussian product centre
+    double PAx, PAy, PAz; // P - A   (A = centre of the first shell of the pair)
+    double cc;            // c_i c_j exp(-a_i a_j |AB|^2 / p)
+};
+struct ShellPair {  // 48 bytes
+    double ABx, ABy, ABz;  // A - B
+    double q;              // Schwarz bound sqrt(max |(ab|ab)|) over Cartesian components
+    int32_t ish, jsh;      // device shell ids
+    int32_t i0, j0;        // Cartesian AO offsets
+    int32_t prim_off, nprim;
+    int32_t same;          // ish == jsh
+    int32_t pad;
+};
+
+// ---------------------------------------------------------------------------------------------
+template <int LI_, int LJ_, int LK_, int LL_, int NP_>
+struct QClass {
+    static constexpr int LI = LI_, LJ = LJ_, LK = LK_, LL = LL_, NP = NP_;
+    static constexpr int NI = ncart(LI), NJ = ncart(LJ), NK = ncart(LK), NL = ncart(LL);
+    static_assert(NJ % NP == 0, "NP must divide the number of j components");
+    static constexpr int NJP = NJ / NP;
+    static constexpr int NV = NI * NJP;   // register accumulators per thread
+    static constexpr int NKL = NK * NL;
+    static constexpr int G = NKL * NP;    // threads per quartet
+    static constexpr int NR = (LI + LJ + LK + LL) / 2 + 1;
+    static constexpr int LB = LI + LJ, LT = LK + LL, NB1 = LB + 1, NT1 = LT + 1, ISZ = NB1 * NT1;
+    static constexpr int NI1 = LI + 1, NJ1 = LJ + 1;
+};
+
+template <class C>
+struct SlotSmem {
+    double I[3][C::NR][C::ISZ];  // VRR output I[n*NT1+m]; z carries weight*prefactor
+    double U[C::NR], W[C::NR];
+    double pc[12];               // p, q, PA[3], QC[3], PQ[3], pad
+    double ccd[3][C::LL + 1][C::LL + 1];  // binom(l,t) CD^(l-t)
+    double fac;                  // symmetry factor (1, 1/2, 1/4, 1/8)
+    int32_t kl, k0, l0, nprim_k, prim_off_k, active, pact, pad;
+};
+
+struct BraInfo {
+    double ABx, ABy, ABz;
+    int32_t i0, j0, nprim, prim_off, same, idx;
+};
+
+template <class C>
+struct ThreadCtx {
+    int q, g, p, c, d;
+    int kx, ky, kz, lx, ly, lz;
+    double v[C::NV];
+};
+
+template <class C>
+B2_HD void thread_decode(ThreadCtx<C>& t, int tid)
+{
+    t.q = tid / C::G;
+    t.g = tid % C::G;
+    t.p = t.g / C::NKL;
+    int cd = t.g % C::NKL;
+    t.c = cd % C::NK;
+    t.d = cd / C::NK;
+    t.kx = cart_px(C::LK, t.c); t.ky = cart_py(C::LK, t.c); t.kz = C::LK - t.kx - t.ky;
+    t.lx = cart_px(C::LL, t.d); t.ly = cart_py(C::LL, t.d); t.lz = C::LL - t.lx - t.ly;
+}
+
+// per-ket-slot constants: binom(l,t) * CD^(l-t)
+template <class C>
+B2_HD void slot_set_cd(SlotSmem<C>& s, double CDx, double CDy, double CDz)
+{
+    double cd[3] = {CDx, CDy, CDz};
+    for (int x = 0; x < 3; x++)
+        for (int l = 0; l <= C::LL; l++) {
+            // binom(l,t) CD^(l-t), zero for t>l
+            double binom = 1.0;
+            for (int t = 0; t <= C::LL; t++) {
+                if (t > l) { s.ccd[x][l][t] = 0.0; continue; }
+                double pw = 1.0;
+                for (int e = 0; e < l - t; e++) pw *= cd[x];
+                s.ccd[x][l][t] = binom * pw;
+                binom = binom * (l - t) / (t + 1);
+            }
+        }
+}
+
+// Phase A: Rys roots for primitive quartet (bp, kp).  Threads g, g+G, ... < NR of the slot.
+template <class C>
+B2_HD void phase_roots(SlotSmem<C>& s, int g, const PrimPair& bp, const PrimPair& kp, const RysTables& tb, double omega)
+{
+    double p = bp.p, q = kp.p;
+    double PQx = bp.Px - kp.Px, PQy = bp.Py - kp.Py, PQz = bp.Pz - kp.Pz;
+    double pq = p + q;
+    double rho = p * q / pq;
+    double x = rho * (PQx * PQx + PQy * PQy + PQz * PQz);
+    double pref = PI_25_2 / (p * q * sqrt(pq)) * bp.cc * kp.cc;
+    double theta = 1.0;
+    if (omega > 0.0) {  // erf(omega r)/r: evaluate at x*theta, u*theta, w*sqrt(theta)
+        theta = omega * omega / (omega * omega + rho);
+        x *= theta;
+        pref *= sqrt(theta);
+    }
+    for (int r = g; r < C::NR; r += C::G) {
+        double u, w;
+        rys_root(tb, C::NR, r, x, u, w);
+        s.U[r] = u * theta;
+        s.W[r] = w * pref;
+    }
+    if (g == 0) {
+        s.pc[0] = p; s.pc[1] = q;
+        s.pc[2] = bp.PAx; s.pc[3] = bp.PAy; s.pc[4] = bp.PAz;
+        s.pc[5] = kp.PAx; s.pc[6] = kp.PAy; s.pc[7] = kp.PAz;
+        s.pc[8] = PQx; s.pc[9] = PQy; s.pc[10] = PQz;
+    }
+}
+
+// Phase B: vertical recurrence for (root r, direction x) tasks g, g+G, ... < 3*NR
+template <class C>
+B2_HD void phase_vrr(SlotSmem<C>& s, int g)
+{
+    double p = s.pc[0], q = s.pc[1];
+    double ipq = 1.0 / (p + q);
+    for (int task = g; task < 3 * C::NR; task += C::G) {
+        int r = task / 3, x = task - 3 * r;
+        double u = s.U[r];
+        double b00 = 0.5 * u * ipq;
+        double b10 = (1.0 - u * q * ipq) * (0.5 / p);
+        double b01 = (1.0 - u * p * ipq) * (0.5 / q);
+        double c00 = s.pc[2 + x] - u * q * ipq * s.pc[8 + x];
+        double c0p = s.pc[5 + x] + u * p * ipq * s.pc[8 + x];
+        double* I = s.I[x][r];
+        constexpr int NT1 = C::NT1;
+        double i0 = (x == 2) ? s.W[r] : 1.0;
+        I[0] = i0;
+        if (C::LB > 0) {
+            double im1 = i0, in = c00 * i0;
+            I[NT1] = in;
+            B2_UNROLL
+            for (int n = 1; n < C::LB; n++) {
+                double nx = c00 * in + n * b10 * im1;
+                I[(n + 1) * NT1] = nx;
+                im1 = in; in = nx;
+            }
+        }
+        B2_UNROLL
+        for (int m = 0; m < C::LT; m++) {
+            B2_UNROLL
+            for (int n = 0; n <= C::LB; n++) {
+                double val = c0p * I[n * NT1 + m];
+                if (m > 0) val += m * b01 * I[n * NT1 + m - 1];
+                if (n > 0) val += n * b00 * I[(n - 1) * NT1 + m];
+                I[n * NT1 + m + 1] = val;
+            }
+        }
+    }
+}
+
+// thread-local horizontal recurrences for one direction: out[j*(LI+1)+i]
+template <class C>
+B2_HD void hrr_dir(const double* I, int k, int l, const double (*ccd)[C::LL + 1], double AB, double* out)
+{
+    double T[C::NB1];
+    B2_UNROLL
+    for (int n = 0; n <= C::LB; n++) {
+        double sacc = 0.0;
+        B2_UNROLL
+        for (int t = 0; t <= C::LL; t++) sacc += ccd[l][t] * I[n * C::NT1 + k + t];
+        T[n] = sacc;
+    }
+    B2_UNROLL
+    for (int i = 0; i <= C::LI; i++) out[i] = T[i];
+    B2_UNROLL
+    for (int j = 1; j <= C::LJ; j++) {
+        B2_UNROLL
+        for (int n = 0; n <= C::LB - j; n++) T[n] = T[n + 1] + AB * T[n];
+        B2_UNROLL
+        for (int i = 0; i <= C::LI; i++) out[j * C::NI1 + i] = T[i];
+    }
+}
+
+template <class C, int P>
+B2_HD void accumulate_part(double* v, const double* gx, const double* gy, const double* gz)
+{
+    B2_UNROLL
+    for (int bb = 0; bb < C::NJP; bb++) {
+        B2_UNROLL
+        for (int a = 0; a < C::NI; a++) {
+            constexpr int dummy = 0; (void)dummy;
+            const int b = P * C::NJP + bb;
+            const int ix = cart_px(C::LI, a), iy = cart_py(C::LI, a), iz = C::LI - ix - iy;
+            const int jx = cart_px(C::LJ, b), jy = cart_py(C::LJ, b), jz = C::LJ - jx - jy;
+            v[bb * C::NI + a] += gx[jx * C::NI1 + ix] * gy[jy * C::NI1 + iy] * gz[jz * C::NI1 + iz];
+        }
+    }
+}
+
+template <class C, int P>
+struct PartDispatch {
+    static B2_HD void run(int p, double* v, const double* gx, const double* gy, const double* gz)
+    {
+        if (p == P) accumulate_part<C, P>(v, gx, gy, gz);
+        else PartDispatch<C, P + 1>::run(p, v, gx, gy, gz);
+    }
+};
+template <class C>
+struct PartDispatch<C, C::NP> {
+    static B2_HD void run(int, double*, const double*, const double*, const double*) {}
+};
+
+// Phase D: every thread of the slot
+template <class C>
+B2_HD void phase_accumulate(const SlotSmem<C>& s, ThreadCtx<C>& t, double ABx, double ABy, double ABz)
+{
+    for (int r = 0; r < C::NR; r++) {
+        double gx[C::NI1 * C::NJ1], gy[C::NI1 * C::NJ1], gz[C::NI1 * C::NJ1];
+        hrr_dir<C>(s.I[0][r], t.kx, t.lx, s.ccd[0], ABx, gx);
+        hrr_dir<C>(s.I[1][r], t.ky, t.ly, s.ccd[1], ABy, gy);
+        hrr_dir<C>(s.I[2][r], t.kz, t.lz, s.ccd[2], ABz, gz);
+        PartDispatch<C, 0>::run(t.p, t.v, gx, gy, gz);
+    }
+}
+
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ void red_add(double* addr, double val) { atomicAdd(addr, val); }
+#else
+inline void red_add(double* addr, double val) { *addr += val; }
+#endif
+
+// Phase E: contract the register block with the density and flush.
+//   Jacc[ij] += 2 f v D[kl] ; Jacc[kl] += 2 f v D[ij]            (J = Jacc + Jacc^T)
+//   Kacc[ik] += f v D[jl] ; Kacc[il] += f v D[jk] ; Kacc[jk] += f v D[il] ; Kacc[jl] += f v D[ik]
+//                                                                 (K = Kacc +/- Kacc^T)
+// dmj/dmk: [n_dm][n][n] Cartesian; dmj symmetric; dmk symmetric or antisymmetric.
+template <class C>
+B2_HD void phase_digest(const SlotSmem<C>& s, const ThreadCtx<C>& t, int i0, int j0, int n, int n_dm,
+                        const double* dmj, const double* dmk, double* vj, double* vk)
+{
+    const double f = s.fac;
+    const int kc = s.k0 + t.c, ld = s.l0 + t.d;
+    const int b0 = t.p * C::NJP;
+    const size_t n2 = (size_t)n * n;
+    for (int idm = 0; idm < n_dm; idm++) {
+        if (vj) {
+            const double* D = dmj + idm * n2;
+            double* J = vj + idm * n2;
+            double dkl = 2.0 * f * D[(size_t)kc * n + ld];
+            double jkl = 0.0;
+            B2_UNROLL
+            for (int bb = 0; bb < C::NJP; bb++) {
+                B2_UNROLL
+                for (int a = 0; a < C::NI; a++) {
+                    double val = t.v[bb * C::NI + a];
+                    size_t ij = (size_t)(i0 + a) * n + (j0 + b0 + bb);
+                    jkl += val * D[ij];
+                    red_add(&J[ij], val * dkl);
+                }
+            }
+            red_add(&J[(size_t)kc * n + ld], 2.0 * f * jkl);
+        }
+        if (vk) {
+            const double* D = dmk + idm * n2;
+            double* K = vk + idm * n2;
+            double kjk[C::NJP], kjl[C::NJP];
+            double kik[C::NI], kil[C::NI];
+            double dik[C::NI], dil[C::NI];
+            B2_UNROLL
+            for (int a = 0; a < C::NI; a++) {
+                kik[a] = 0.0; kil[a] = 0.0;
+                dik[a] = D[(size_t)(i0 + a) * n + kc];
+                dil[a] = D[(size_t)(i0 + a) * n + ld];
+            }
+            B2_UNROLL
+            for (int bb = 0; bb < C::NJP; bb++) {
+                int jb = j0 + b0 + bb;
+                double djl = D[(size_t)jb * n + ld], djk = D[(size_t)jb * n + kc];
+                double sjk = 0.0, sjl = 0.0;
+                B2_UNROLL
+                for (int a = 0; a < C::NI; a++) {
+                    double val = t.v[bb * C::NI + a];
+                    kik[a] += val * djl;
+                    kil[a] += val * djk;
+                    sjk += val * dil[a];
+                    sjl += val * dik[a];
+                }
+                kjk[bb] = sjk; kjl[bb] = sjl;
+            }
+            B2_UNROLL
+            for (int a = 0; a < C::NI; a++) {
+                red_add(&K[(size_t)(i0 + a) * n + kc], f * kik[a]);
+                red_add(&K[(size_t)(i0 + a) * n + ld], f * kil[a]);
+            }
+            B2_UNROLL
+            for (int bb = 0; bb < C::NJP; bb++) {
+                int jb = j0 + b0 + bb;
+                red_add(&K[(size_t)jb * n + kc], f * kjk[bb]);
+                red_add(&K[(size_t)jb * n + ld], f * kjl[bb]);
+            }
+        }
+    }
+}
+
+// Screening decision of CVHFnrs8_prescreen (pyscf/lib/vhf/optimizer.c:90-117) on device shells.
+B2_HD bool keep_quartet(double qij, double qkl, int ish, int jsh, int ksh, int lsh, const double* dmc, int nsh,
+                        double tol, bool do_j, bool do_k)
+{
+    double qq = qij * qkl;
+    if (!(qq > tol)) return false;
+    double dmin = tol / qq;
+    bool keep = false;
+    if (do_j) keep = (4.0 * dmc[ish * nsh + jsh] > dmin) || (4.0 * dmc[ksh * nsh + lsh] > dmin);
+    if (do_k && !keep)
+        keep = (dmc[jsh * nsh + ksh] > dmin) || (dmc[jsh * nsh + lsh] > dmin) || (dmc[ish * nsh + ksh] > dmin) ||
+               (dmc[ish * nsh + lsh] > dmin);
+    return keep;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic (run-time angular momentum) diagonal integrals for the Schwarz bounds:
+//   q = sqrt(max_ab |(ab|ab)|)   <- CVHFnr_int2e_q_cond, pyscf/lib/vhf/optimizer.c:408-454
+B2_HD double schwarz_pair(int la, int lb, const ShellPair& sp, const PrimPair* prims, const RysTables& tb, double omega)
+{
+    const int L = la + lb;          // per side
+    const int nr = L + 1;           // (2L)/2 + 1
+    const int na = ncart(la), nb = ncart(lb);
+    double acc[ncart(LMAX) * ncart(LMAX)];
+    for (int e = 0; e < na * nb; e++) acc[e] = 0.0;
+    double AB[3] = {sp.ABx, sp.ABy, sp.ABz};
+    for (int ip = 0; ip < sp.nprim; ip++)
+        for (int kp = 0; kp < sp.nprim; kp++) {
+            const PrimPair& bp = prims[sp.prim_off + ip];
+            const PrimPair& kq = prims[sp.prim_off + kp];
+            double p = bp.p, q = kq.p, pq = p + q, ipq = 1.0 / pq;
+            double PQ[3] = {bp.Px - kq.Px, bp.Py - kq.Py, bp.Pz - kq.Pz};
+            double PA[3] = {bp.PAx, bp.PAy, bp.PAz}, QC[3] = {kq.PAx, kq.PAy, kq.PAz};
+            double rho = p * q * ipq;
+            double x = rho * (PQ[0] * PQ[0] + PQ[1] * PQ[1] + PQ[2] * PQ[2]);
+            double pref = PI_25_2 / (p * q * sqrt(pq)) * bp.cc * kq.cc;
+            double theta = 1.0;
+            if (omega > 0.0) { theta = omega * omega / (omega * omega + rho); x *= theta; pref *= sqrt(theta); }
+            for (int r = 0; r < nr; r++) {
+                double u, w;
+                rys_root(tb, nr, r, x, u, w);
+                u *= theta; w *= pref;
+                double I[3][2 * LMAX + 1][2 * LMAX + 1];
+                double b00 = 0.5 * u * ipq, b10 = (1.0 - u * q * ipq) * 0.5 / p, b01 = (1.0 - u * p * ipq) * 0.5 / q;
+                for (int d = 0; d < 3; d++) {
+                    double c00 = PA[d] - u * q * ipq * PQ[d], c0p = QC[d] + u * p * ipq * PQ[d];
+                    I[d][0][0] = (d == 2) ? w : 1.0;
+                    if (L > 0) I[d][1][0] = c00 * I[d][0][0];
+                    for (int n = 1; n < L; n++) I[d][n + 1][0] = c00 * I[d][n][0] + n * b10 * I[d][n - 1][0];
+                    for (int m = 0; m < L; m++)
+                        for (int n = 0; n <= L; n++) {
+                            double val = c0p * I[d][n][m];
+                            if (m > 0) val += m * b01 * I[d][n][m - 1];
+                            if (n > 0) val += n * b00 * I[d][n - 1][m];
+                            I[d][n][m + 1] = val;
+                        }
+                }
+                for (int b = 0; b < nb; b++)
+                    for (int a = 0; a < na; a++) {
+                        int ia[3] = {cart_px(la, a), cart_py(la, a), 0};
+                        ia[2] = la - ia[0] - ia[1];
+                        int jb[3] = {cart_px(lb, b), cart_py(lb, b), 0};
+                        jb[2] = lb - jb[0] - jb[1];
+                        double prod = 1.0;
+                        for (int d = 0; d < 3; d++) {
+                            // G(i,j,i,j) = sum_s sum_t C(j,s)C(j,t) AB^(2j-s-t) I[i+s][i+t]
+                            double gsum = 0.0;
+                            double bs = 1.0;
+                            for (int s_ = 0; s_ <= jb[d]; s_++) {
+                                double ps = 1.0;
+                                for (int e = 0; e < jb[d] - s_; e++) ps *= AB[d];
+                                double bt = 1.0;
+                                for (int t_ = 0; t_ <= jb[d]; t_++) {
+                                    double pt = 1.0;
+                                    for (int e = 0; e < jb[d] - t_; e++) pt *= AB[d];
+                                    gsum += bs * ps * bt * pt * I[d][ia[d] + s_][ia[d] + t_];
+                                    bt = bt * (jb[d] - t_) / (t_ + 1);
+                                }
+                                bs = bs * (jb[d] - s_) / (s_ + 1);
+                            }
+                            prod *= gsum;
+                        }
+                        acc[b * na + a] += prod;
+                    }
+            }
+        }
+    double m = 0.0;
+    for (int e = 0; e < na * nb; e++) m = fmax(m, fabs(acc[e]));
+    return sqrt(m);
+}
+
+}  // namespace b200jk

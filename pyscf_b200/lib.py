@@ -1,0 +1,107 @@
+"""ctypes binding of libb200jk.so (C ABI: include/b200jk.h).
+
+This is the only place the product loads native code.  There is no CPU fallback: if the CUDA
+library is missing or no GPU is present the calls raise RuntimeError (SURVEY.md §8b error
+conventions; reference analogue: lib.load_library, pyscf/lib/misc.py:123).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, 'libb200jk.so')
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int_p = ctypes.POINTER(ctypes.c_int32)
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [('ms_total', ctypes.c_double), ('ms_kernels', ctypes.c_double), ('ms_h2d', ctypes.c_double),
+                ('ms_d2h', ctypes.c_double), ('quartets_computed', ctypes.c_uint64),
+                ('quartets_screened', ctypes.c_uint64), ('kernel_launches', ctypes.c_uint64),
+                ('n_dev_shells', ctypes.c_int32), ('n_cart', ctypes.c_int32), ('n_sph', ctypes.c_int32),
+                ('n_pairs', ctypes.c_int32)]
+
+
+_libs = {}
+
+SYMBOLS = ['b200jk_create', 'b200jk_destroy', 'b200jk_set_screening', 'b200jk_direct_jk', 'b200jk_direct_jk_device',
+           'b200jk_df_build', 'b200jk_df_jk', 'b200jk_df_naux', 'b200jk_get_q_cond', 'b200jk_get_stats',
+           'b200jk_last_error', 'b200jk_version']
+
+
+def load(path=None):
+    path = path or DEFAULT_LIB
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise RuntimeError('libb200jk.so not found at %s: build it with `python -c "import __graft_entry__ as g; '
+                           'g.build()"`; pyscf_b200 has no CPU fallback' % path)
+    lib = ctypes.CDLL(path)
+    vp = ctypes.c_void_p
+    lib.b200jk_create.argtypes = [ctypes.POINTER(vp), c_int_p, ctypes.c_int, c_int_p, ctypes.c_int, c_double_p,
+                                  ctypes.c_int, ctypes.c_int]
+    lib.b200jk_destroy.argtypes = [vp]
+    lib.b200jk_set_screening.argtypes = [vp, ctypes.c_double, ctypes.c_double]
+    lib.b200jk_direct_jk.argtypes = [vp, c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p]
+    lib.b200jk_direct_jk_device.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
+    lib.b200jk_df_build.argtypes = [vp, c_int_p, ctypes.c_int, c_int_p, ctypes.c_int, c_double_p, ctypes.c_int,
+                                    ctypes.c_double, ctypes.c_double]
+    lib.b200jk_df_jk.argtypes = [vp, c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_int,
+                                 c_double_p, c_double_p]
+    lib.b200jk_df_naux.argtypes = [vp, ctypes.POINTER(ctypes.c_int)]
+    lib.b200jk_get_q_cond.argtypes = [vp, c_double_p, ctypes.c_int]
+    lib.b200jk_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    lib.b200jk_last_error.argtypes = [vp]
+    lib.b200jk_last_error.restype = ctypes.c_char_p
+    lib.b200jk_version.restype = ctypes.c_char_p
+    _libs[path] = lib
+    return lib
+
+
+def dptr(a):
+    return None if a is None else a.ctypes.data_as(c_double_p)
+
+
+def iptr(a):
+    return a.ctypes.data_as(c_int_p)
+
+
+class Handle:
+    """Owns one b200jk_handle (device memory for one molecule/basis)."""
+
+    def __init__(self, atm, bas, env, device=0, libpath=None):
+        self.lib = load(libpath)
+        self._h = ctypes.c_void_p()
+        self.atm = np.ascontiguousarray(atm, dtype=np.int32)
+        self.bas = np.ascontiguousarray(bas, dtype=np.int32)
+        self.env = np.ascontiguousarray(env, dtype=np.float64)
+        rc = self.lib.b200jk_create(ctypes.byref(self._h), iptr(self.atm), len(self.atm), iptr(self.bas),
+                                    len(self.bas), dptr(self.env), len(self.env), device)
+        if rc != 0:
+            msg = self.lib.b200jk_last_error(self._h).decode() if self._h else 'b200jk_create failed'
+            if self._h:
+                self.lib.b200jk_destroy(self._h)
+                self._h = ctypes.c_void_p()
+            raise RuntimeError('b200jk_create: ' + msg)
+
+    def check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError('%s: %s' % (what, self.lib.b200jk_last_error(self._h).decode()))
+
+    def stats(self):
+        s = Stats()
+        self.lib.b200jk_get_stats(self._h, ctypes.byref(s))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def close(self):
+        if getattr(self, '_h', None) and self._h:
+            self.lib.b200jk_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
