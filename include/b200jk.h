@@ -75,6 +75,16 @@ int b200jk_df_naux(b200jk_handle h, int* naux);
 /* Schwarz table q_cond[nbas,nbas] in the reference's (contracted, spherical-order) shell indexing. */
 int b200jk_get_q_cond(b200jk_handle h, double* q_cond, int nbas);
 
+/* Run all work of this handle on the caller's CUDA stream (cudaStream_t cast to void*); NULL restores the
+ * handle's own stream.  Lets a host framework (e.g. torch) order and time the calls with its own events. */
+int b200jk_set_stream(b200jk_handle h, void* cuda_stream);
+/* Register-resident DFMA micro-benchmark: measured FP64 FMA-pipe peak (TFLOP/s) of the handle's device,
+ * the roofline denominator of the 4-center path (MEASURED_PEAKS.json has no fp64 entry). */
+int b200jk_fp64_peak(b200jk_handle h, double* tflops);
+/* Per-class kernel timing (CUDA events around each class launch; adds sync points, off by default).
+ * ms[100]: entry [cb*10+ck], pair class id = l1*(l1+1)/2+l2 (ss,ps,pp,ds,dp,dd,fs,fp,fd,ff). */
+int b200jk_set_profile(b200jk_handle h, int on);
+int b200jk_get_class_times(b200jk_handle h, double* ms, int n);
 int b200jk_get_stats(b200jk_handle h, b200jk_stats* out);
 const char* b200jk_last_error(b200jk_handle h);
 const char* b200jk_version(void);

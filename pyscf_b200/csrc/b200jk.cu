@@ -166,8 +166,12 @@ struct b200jk_handle_s {
     b200jk_stats stats{};
 #ifndef B200JK_EMULATE
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> cls_ev;
 #endif
+    int profile = 0;
+    double class_ms[NPC * NPC] = {0};
 };
 
 namespace {
@@ -320,7 +324,8 @@ extern "C" int b200jk_create(b200jk_handle* out, const int32_t* atm, int natm, c
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
             throw std::runtime_error("no CUDA device: libb200jk has no CPU fallback");
         CK(cudaSetDevice(device));
-        CK(cudaStreamCreate(&h->stream));
+        CK(cudaStreamCreate(&h->own_stream));
+        h->stream = h->own_stream;
         CK(cudaEventCreate(&h->ev0));
         CK(cudaEventCreate(&h->ev1));
 #endif
@@ -448,7 +453,7 @@ extern "C" int b200jk_destroy(b200jk_handle h)
 #ifndef B200JK_EMULATE
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
 #endif
     delete h;
     return 0;
@@ -573,7 +578,16 @@ static int direct_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, 
                 P.bra_pairs = B.d_kept; P.nbra = (int)B.kept.size();
                 P.ket_pairs = K.d_kept; P.nket = (int)K.kept.size();
                 P.same_class = (cb == ck);
+#ifndef B200JK_EMULATE
+                if (h->profile) {
+                    if (h->cls_ev.empty()) { h->cls_ev.resize(2 * NPC * NPC); for (auto& e : h->cls_ev) CK(cudaEventCreate(&e)); }
+                    CK(cudaEventRecord(h->cls_ev[2 * (cb * NPC + ck)], st));
+                }
+#endif
                 launch_class(cb, ck, P, st);
+#ifndef B200JK_EMULATE
+                if (h->profile) CK(cudaEventRecord(h->cls_ev[2 * (cb * NPC + ck) + 1], st));
+#endif
                 launches++;
             }
 #ifndef B200JK_EMULATE
@@ -603,6 +617,15 @@ static int direct_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, 
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         h->stats.ms_kernels = ms;
+        if (h->profile)
+            for (int cb = 0; cb < NPC; cb++)
+                for (int ck = 0; ck <= cb; ck++) {
+                    h->class_ms[cb * NPC + ck] = 0.0;
+                    if (h->pc[cb].kept.empty() || h->pc[ck].kept.empty()) continue;
+                    float cm = 0;
+                    CK(cudaEventElapsedTime(&cm, h->cls_ev[2 * (cb * NPC + ck)], h->cls_ev[2 * (cb * NPC + ck) + 1]));
+                    h->class_ms[cb * NPC + ck] = cm;
+                }
 #endif
         auto t1 = std::chrono::steady_clock::now();
         h->stats.ms_total = std::chrono::duration<double, std::milli>(t1 - t0).count();
@@ -620,6 +643,70 @@ extern "C" int b200jk_direct_jk(b200jk_handle h, const double* dm, int n_dm, int
 extern "C" int b200jk_direct_jk_device(b200jk_handle h, const double* dm, int n_dm, int nao, int hermi, double* vj, double* vk)
 {
     return direct_jk_impl(h, dm, n_dm, nao, hermi, vj, vk, true);
+}
+
+extern "C" int b200jk_set_profile(b200jk_handle h, int on) { if (!h) return 1; h->profile = on; return 0; }
+extern "C" int b200jk_get_class_times(b200jk_handle h, double* ms, int n)
+{
+    if (!h || !ms || n != NPC * NPC) return 1;
+    memcpy(ms, h->class_ms, sizeof(double) * n);
+    return 0;
+}
+
+extern "C" int b200jk_set_stream(b200jk_handle h, void* stream)
+{
+    if (!h) return 1;
+#ifndef B200JK_EMULATE
+    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+#else
+    (void)stream;
+#endif
+    return 0;
+}
+
+#ifndef B200JK_EMULATE
+// register-resident DFMA chains: the FP64 roofline denominator of the 4-center path
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+#endif
+
+extern "C" int b200jk_fp64_peak(b200jk_handle h, double* tflops)
+{
+    if (!h || !tflops) return 1;
+#ifndef B200JK_EMULATE
+    try {
+        CK(cudaSetDevice(h->device));
+        int nsm = 0;
+        CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device));
+        int blocks = nsm * 8, iters = 1 << 15;
+        double* buf = (double*)dev_alloc((size_t)blocks * 256 * 8);
+        double best = 0;
+        for (int rep = 0; rep < 5; rep++) {
+            CK(cudaEventRecord(h->ev0, h->stream));
+            fp64_peak_kernel<<<blocks, 256, 0, h->stream>>>(buf, iters);
+            CK(cudaEventRecord(h->ev1, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            double tf = 2.0 * 8 * iters * (double)blocks * 256 / (ms * 1e-3) / 1e12;
+            if (tf > best) best = tf;
+        }
+        dev_free(buf);
+        *tflops = best;
+    } catch (std::exception& e) { set_err(h, e.what()); return 2; }
+    return 0;
+#else
+    *tflops = 0.0;
+    return 0;
+#endif
 }
 
 extern "C" int b200jk_get_stats(b200jk_handle h, b200jk_stats* out)

@@ -219,3 +219,10 @@ def load_xyz(path):
         lines = f.read().splitlines()
     n = int(lines[0].split()[0])
     return [(t.split()[0], [float(x) for x in t.split()[1:4]]) for t in lines[2:2 + n]]
+
+
+def geometry(name):
+    """Atoms of a committed benchmark geometry (pyscf_b200/data/geom/<name>.xyz, Angstrom)."""
+    import os
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return load_xyz(os.path.join(here, 'data', 'geom', name + '.xyz'))

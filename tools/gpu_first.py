@@ -3,7 +3,8 @@ import numpy as np
 from pyscf_b200 import gto
 from pyscf_b200.jk import VHFOpt
 from oracle import oracle as O
-from tests.conftest import H2O, BENZENE
+from pyscf_b200.gto.mole import geometry
+BENZENE = geometry("benzene")
 import __graft_entry__ as g
 g.smoke()
 for basis in ['cc-pvdz','cc-pvtz']:
