@@ -506,7 +506,10 @@ extern "C" int b200jk_get_q_cond(b200jk_handle h, double* q, int nbas)
     for (int c = 0; c < NPC; c++)
         for (auto& sp : h->pc[c].all) {
             int I = h->ref_shell_of[sp.ish], J = h->ref_shell_of[sp.jsh];
-            double v = std::max(sp.q, 1e-100);
+            // device bounds are over bare Cartesian monomials; rescale to the reference's normalised AOs
+            // (exact for s and p, where cart->sph is a multiple of the identity; an estimate for l >= 2)
+            auto fl = [](int l) { auto T = make_c2s(l); double m = 0; for (double t : T) m = std::max(m, std::fabs(t)); return m; };
+            double v = std::max(sp.q * fl(h->sh[sp.ish].l) * fl(h->sh[sp.jsh].l), 1e-100);
             q[(long)I * nbas + J] = std::max(q[(long)I * nbas + J], v);
             q[(long)J * nbas + I] = std::max(q[(long)J * nbas + I], v);
         }

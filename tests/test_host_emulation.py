@@ -138,4 +138,5 @@ def test_emulated_screening_and_errors(emu_lib):
         opt.get_jk(np.zeros((nao + 1, nao + 1)))
     q = opt.q_cond
     qo = O.q_cond(mol)
-    assert q.shape == qo.shape and abs(np.log(q / qo)).max() < 0.7  # Cartesian vs spherical bound
+    big = qo > 1e-12  # negligible pairs are dropped on the device side (reported as the 1e-100 floor)
+    assert q.shape == qo.shape and abs(np.log(q[big] / qo[big])).max() < 1e-9  # s,p: identical to CVHFnr_int2e_q_cond
