@@ -416,7 +416,7 @@ extern "C" int b200jk_create(b200jk_handle* out, const int32_t* atm, int natm, c
                         pp.p = p;
                         pp.Px = (ea * a.r[0] + eb * b.r[0]) / p; pp.Py = (ea * a.r[1] + eb * b.r[1]) / p; pp.Pz = (ea * a.r[2] + eb * b.r[2]) / p;
                         pp.PAx = pp.Px - a.r[0]; pp.PAy = pp.Py - a.r[1]; pp.PAz = pp.Pz - a.r[2];
-                        pp.cc = cc;
+                        pp.cc = cc / p * 5.914967172795612486;  // sqrt(2 pi^(5/2)) folded in, see phase_roots
                         h->prims.push_back(pp);
                         np++;
                     }
@@ -488,7 +488,9 @@ extern "C" int b200jk_set_screening(b200jk_handle h, double tol, double omega)
             // applied per quartet on device; keep the Schwarz-only bound here, like q_cond in the reference)
             for (auto& sp : P.all)
                 if (sp.q * qmax > tol * 1e-2) P.kept.push_back(sp);
-            std::stable_sort(P.kept.begin(), P.kept.end(), [](const ShellPair& a, const ShellPair& b) { return a.q > b.q; });
+            // batches of kets are homogeneous in primitive count (groups iterate to the longest slot), then by bound
+            std::stable_sort(P.kept.begin(), P.kept.end(), [](const ShellPair& a, const ShellPair& b) {
+                return a.nprim != b.nprim ? a.nprim > b.nprim : a.q > b.q; });
             dev_free(P.d_kept);
             P.d_kept = upload(P.kept);
         }

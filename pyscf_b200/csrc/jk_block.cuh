@@ -1,6 +1,13 @@
 // jk_block.cuh — the CTA-level procedure of the direct J/K kernels (one template per class).
-// Compiles as a CUDA kernel body (threads = CUDA threads, B2_SYNC = __syncthreads) and, with
-// B200JK_EMULATE, as a sequential SIMT emulation on the CPU (tests only).
+//
+// A CTA owns ONE bra shell pair and a chunk of the ket-pair list, which it screens on device and
+// compacts into shared memory.  Inside the CTA, independent thread GROUPS (a sub-warp, one warp, or a
+// few warps joined by a named barrier) pull batches of ket pairs from a shared counter; a group only
+// ever synchronises with itself, so there is no block-wide lock-step over primitive loops.
+// J[ij] for the stationary bra pair is accumulated in registers across all kets and flushed once.
+//
+// Compiles as a CUDA kernel body and, with B200JK_EMULATE, as a sequential SIMT emulation on the CPU
+// (tests only): groups run one after the other and every phase is a loop over the group's lanes.
 #pragma once
 #include "jk_core.cuh"
 
@@ -23,101 +30,100 @@ struct KParams {
     unsigned long long* counters;  // [0] quartets computed, [1] quartets screened out (may be null)
 };
 
-template <class C, int NQ>
+constexpr int pow2ceil(int x) { int p = 1; while (p < x) p *= 2; return p; }
+
+template <class C>
+struct GroupCfg {
+    static constexpr int G = C::G;
+    static constexpr int GP = G <= 32 ? pow2ceil(G) : ((G + 31) / 32) * 32;  // lanes reserved per quartet
+    static constexpr int GW = (GP + 31) / 32;                                // warps per group
+    static constexpr int TG = GW * 32;                                       // threads per group
+    static constexpr int QPG = GP <= 32 ? 32 / GP : 1;                       // quartets in flight per group
+    static constexpr int NG0 = 192 / TG;
+    static constexpr int NG = NG0 < 1 ? 1 : (NG0 > 8 ? 8 : NG0);             // groups per CTA
+    static constexpr int NT = NG * TG;
+    static constexpr int NSLOT = NG * QPG;
+};
+
+template <class C>
 struct BlockSmem {
-    SlotSmem<C> slot[NQ];
+    SlotSmem<C> slot[GroupCfg<C>::NSLOT];
     BraInfo bra;
     int klist[KCH_MAX];
     int nk;
-    int npmax;
+    int next;
+    int gbase[GroupCfg<C>::NG];
 };
 
-template <class C, int NQ>
-struct BlockCfg {
-    static constexpr int NT = ((NQ * C::G + 31) / 32) * 32;
+template <class C>
+struct LaneCtx {
+    ThreadCtx<C> t;
+    double jij[C::NV];
+    int grp, lt, slot, valid;
+    int ibp, ikp;
 };
 
 #if defined(__CUDA_ARCH__)
-#define B2_FOR_THREADS(tid) { const int tid = threadIdx.x;
-#define B2_END_THREADS }
+#define B2_ALL_THREADS(tid) { const int tid = threadIdx.x;
+#define B2_END }
 #define B2_SYNC() __syncthreads()
+#define B2_GROUP_LANES(lt) { const int lt = threadIdx.x % GroupCfg<C>::TG;
 #define B2_CTX(tid) ctx
-#define B2_DECL_CTX ThreadCtx<C> ctx;
+template <class C>
+__device__ __forceinline__ void group_sync(int grp)
+{
+    if constexpr (GroupCfg<C>::GW == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(GroupCfg<C>::TG) : "memory");
+}
 #else
-#define B2_FOR_THREADS(tid) for (int tid = 0; tid < BlockCfg<C, NQ>::NT; tid++) {
-#define B2_END_THREADS }
+#define B2_ALL_THREADS(tid) for (int tid = 0; tid < GroupCfg<C>::NT; tid++) {
+#define B2_END }
 #define B2_SYNC()
+#define B2_GROUP_LANES(lt) for (int lt = 0; lt < GroupCfg<C>::TG; lt++) {
 #define B2_CTX(tid) ctxs[tid]
-#define B2_DECL_CTX ThreadCtx<C>* ctxs = new ThreadCtx<C>[BlockCfg<C, NQ>::NT];
+template <class C>
+inline void group_sync(int) {}
 #endif
 
-template <class C, int NQ>
+// One group's life: pull ket batches until the CTA's list is exhausted.
+template <class C>
 #ifdef __CUDACC__
 __device__ __forceinline__
 #else
 inline
 #endif
-void jk_block(const KParams& P, int bx, int by, BlockSmem<C, NQ>& sm)
+void group_proc(const KParams& P, BlockSmem<C>& sm, int grp, int nk, int bx,
+#if defined(__CUDA_ARCH__)
+                LaneCtx<C>& ctx
+#else
+                LaneCtx<C>* ctxs
+#endif
+)
 {
-    B2_DECL_CTX
-    const ShellPair& bpair = P.bra_pairs[bx];
-    const int kmax = P.same_class ? (bx + 1) : P.nket;
-    const int kbeg = by * P.kchunk;
-    const int kend = (kbeg + P.kchunk < kmax) ? kbeg + P.kchunk : kmax;
-    if (kbeg >= kend) {
-#if !defined(__CUDA_ARCH__)
-        delete[] ctxs;
-#endif
-        return;
-    }
-
-    B2_FOR_THREADS(tid)
-        thread_decode<C>(B2_CTX(tid), tid);
-        if (tid == 0) {
-            sm.bra.ABx = bpair.ABx; sm.bra.ABy = bpair.ABy; sm.bra.ABz = bpair.ABz;
-            sm.bra.i0 = bpair.i0; sm.bra.j0 = bpair.j0;
-            sm.bra.nprim = bpair.nprim; sm.bra.prim_off = bpair.prim_off;
-            sm.bra.same = bpair.same; sm.bra.idx = bx;
-            sm.nk = 0;
-        }
-    B2_END_THREADS
-    B2_SYNC();
-
-    // ---- on-device screening: compact the surviving kets of this chunk
-    B2_FOR_THREADS(tid)
-        for (int kk = kbeg + tid; kk < kend; kk += BlockCfg<C, NQ>::NT) {
-            const ShellPair& kp = P.ket_pairs[kk];
-            bool keep = keep_quartet(bpair.q, kp.q, bpair.ish, bpair.jsh, kp.ish, kp.jsh, P.dmc, P.nsh, P.tol,
-                                     P.vj != nullptr, P.vk != nullptr);
-            if (keep) {
+    using GC = GroupCfg<C>;
+    const int nbp = sm.bra.nprim;
+    const int tid0 = grp * GC::TG;
+    (void)tid0;
+    for (;;) {
+        B2_GROUP_LANES(lt)
+            if (lt == 0) {
 #if defined(__CUDA_ARCH__)
-                int pos = atomicAdd(&sm.nk, 1);
+                sm.gbase[grp] = atomicAdd(&sm.next, GC::QPG);
 #else
-                int pos = sm.nk++;
+                sm.gbase[grp] = sm.next; sm.next += GC::QPG;
 #endif
-                sm.klist[pos] = kk;
             }
-        }
-    B2_END_THREADS
-    B2_SYNC();
-    const int nk = sm.nk;
-#if defined(__CUDA_ARCH__)
-    if (P.counters && threadIdx.x == 0) {
-        atomicAdd(&P.counters[0], (unsigned long long)nk);
-        atomicAdd(&P.counters[1], (unsigned long long)(kend - kbeg - nk));
-    }
-#else
-    if (P.counters) { P.counters[0] += nk; P.counters[1] += kend - kbeg - nk; }
-#endif
-
-    for (int base = 0; base < nk; base += NQ) {
-        // ---- per-batch slot setup
-        B2_FOR_THREADS(tid)
-            ThreadCtx<C>& t = B2_CTX(tid);
-            if (t.q < NQ) {
-                SlotSmem<C>& s = sm.slot[t.q];
-                if (t.g == 0) {
-                    int e = base + t.q;
+        B2_END
+        group_sync<C>(grp);
+        const int base = sm.gbase[grp];
+        if (base >= nk) break;
+        // ---- slot setup
+        B2_GROUP_LANES(lt)
+            LaneCtx<C>& L = B2_CTX(tid0 + lt);
+            if (L.valid) {
+                SlotSmem<C>& s = sm.slot[L.slot];
+                if (L.t.g == 0) {
+                    int e = base + (L.slot - grp * GC::QPG);
                     s.active = (e < nk);
                     if (s.active) {
                         int kk = sm.klist[e];
@@ -135,70 +141,152 @@ void jk_block(const KParams& P, int bx, int by, BlockSmem<C, NQ>& sm)
                     }
                 }
                 B2_UNROLL
-                for (int e = 0; e < C::NV; e++) t.v[e] = 0.0;
+                for (int e = 0; e < C::NV; e++) L.t.v[e] = 0.0;
+                L.ibp = 0; L.ikp = 0;
             }
-            if (tid == 0) sm.npmax = 0;
-        B2_END_THREADS
-        B2_SYNC();
-        B2_FOR_THREADS(tid)
-            if (tid == 0) {
-                int m = 0;
-                for (int q = 0; q < NQ; q++) m = (sm.slot[q].nprim_k > m) ? sm.slot[q].nprim_k : m;
-                sm.npmax = m * sm.bra.nprim;
-            }
-        B2_END_THREADS
-        B2_SYNC();
-        const int npmax = sm.npmax;
-        const int nbp = sm.bra.nprim;
+        B2_END
+        group_sync<C>(grp);
+        int npmax = 0;
+        for (int q = 0; q < GC::QPG; q++) {
+            int nk_ = sm.slot[grp * GC::QPG + q].nprim_k;
+            npmax = nk_ > npmax ? nk_ : npmax;
+        }
+        npmax *= nbp;
 
         for (int ip = 0; ip < npmax; ip++) {
             // ---- phase A: Rys roots
-            B2_FOR_THREADS(tid)
-                ThreadCtx<C>& t = B2_CTX(tid);
-                if (t.q < NQ) {
-                    SlotSmem<C>& s = sm.slot[t.q];
-                    if (s.active) {
-                        int nkp = s.nprim_k;
-                        bool on = ip < nbp * nkp;
-                        if (on) {
-                            int ibp = ip / nkp, ikp = ip - ibp * nkp;
-                            phase_roots<C>(s, t.g, P.prims[sm.bra.prim_off + ibp], P.prims[s.prim_off_k + ikp], P.tb,
-                                           P.omega);
-                        }
+            B2_GROUP_LANES(lt)
+                LaneCtx<C>& L = B2_CTX(tid0 + lt);
+                if (L.valid) {
+                    SlotSmem<C>& s = sm.slot[L.slot];
+                    if (s.active && L.ibp < nbp)
+                        phase_roots<C>(s, L.t.g, P.prims[sm.bra.prim_off + L.ibp], P.prims[s.prim_off_k + L.ikp], P.tb, P.omega);
+                }
+            B2_END
+            group_sync<C>(grp);
+            // ---- phase B: vertical recurrences into shared memory
+            B2_GROUP_LANES(lt)
+                LaneCtx<C>& L = B2_CTX(tid0 + lt);
+                if (L.valid) {
+                    SlotSmem<C>& s = sm.slot[L.slot];
+                    if (s.active && L.ibp < nbp) phase_vrr<C>(s, L.t.g);
+                }
+            B2_END
+            group_sync<C>(grp);
+            // ---- phase D: horizontal recurrences + root sum in registers
+            B2_GROUP_LANES(lt)
+                LaneCtx<C>& L = B2_CTX(tid0 + lt);
+                if (L.valid) {
+                    SlotSmem<C>& s = sm.slot[L.slot];
+                    if (s.active && L.ibp < nbp) {
+                        phase_accumulate<C>(s, L.t, sm.bra.ABx, sm.bra.ABy, sm.bra.ABz);
+                        if (++L.ikp == s.nprim_k) { L.ikp = 0; L.ibp++; }
                     }
                 }
-            B2_END_THREADS
-            B2_SYNC();
-            // ---- phase B: vertical recurrences into shared memory
-            B2_FOR_THREADS(tid)
-                ThreadCtx<C>& t = B2_CTX(tid);
-                if (t.q < NQ) {
-                    SlotSmem<C>& s = sm.slot[t.q];
-                    if (s.active && ip < nbp * s.nprim_k) phase_vrr<C>(s, t.g);
-                }
-            B2_END_THREADS
-            B2_SYNC();
-            // ---- phase D: horizontal recurrences + root sum in registers
-            B2_FOR_THREADS(tid)
-                ThreadCtx<C>& t = B2_CTX(tid);
-                if (t.q < NQ) {
-                    SlotSmem<C>& s = sm.slot[t.q];
-                    if (s.active && ip < nbp * s.nprim_k) phase_accumulate<C>(s, t, sm.bra.ABx, sm.bra.ABy, sm.bra.ABz);
-                }
-            B2_END_THREADS
+            B2_END
         }
         // ---- phase E: digestion
-        B2_FOR_THREADS(tid)
-            ThreadCtx<C>& t = B2_CTX(tid);
-            if (t.q < NQ) {
-                SlotSmem<C>& s = sm.slot[t.q];
+        B2_GROUP_LANES(lt)
+            LaneCtx<C>& L = B2_CTX(tid0 + lt);
+            if (L.valid) {
+                SlotSmem<C>& s = sm.slot[L.slot];
                 if (s.active) {
-                    if (P.vj) phase_digest<C>(s, t, sm.bra.i0, sm.bra.j0, P.n, P.n_dm_j, P.dmj, nullptr, P.vj, nullptr);
-                    if (P.vk) phase_digest<C>(s, t, sm.bra.i0, sm.bra.j0, P.n, P.n_dm_k, nullptr, P.dmk, nullptr, P.vk);
+                    if (P.vj) phase_digest<C>(s, L.t, sm.bra.i0, sm.bra.j0, P.n, P.n_dm_j, P.dmj, nullptr, P.vj, nullptr,
+                                              P.n_dm_j == 1 ? L.jij : nullptr);
+                    if (P.vk) phase_digest<C>(s, L.t, sm.bra.i0, sm.bra.j0, P.n, P.n_dm_k, nullptr, P.dmk, nullptr, P.vk, nullptr);
                 }
             }
-        B2_END_THREADS
-        B2_SYNC();
+        B2_END
+        group_sync<C>(grp);
+    }
+}
+
+template <class C>
+#ifdef __CUDACC__
+__device__ __forceinline__
+#else
+inline
+#endif
+void jk_block(const KParams& P, int bx, int by, BlockSmem<C>& sm)
+{
+    using GC = GroupCfg<C>;
+    const ShellPair& bpair = P.bra_pairs[bx];
+    const int kmax = P.same_class ? (bx + 1) : P.nket;
+    const int kbeg = by * P.kchunk;
+    const int kend = (kbeg + P.kchunk < kmax) ? kbeg + P.kchunk : kmax;
+    if (kbeg >= kend) return;
+#if defined(__CUDA_ARCH__)
+    LaneCtx<C> ctx;
+#else
+    LaneCtx<C>* ctxs = new LaneCtx<C>[GC::NT];
+#endif
+
+    B2_ALL_THREADS(tid)
+        LaneCtx<C>& L = B2_CTX(tid);
+        L.grp = tid / GC::TG;
+        L.lt = tid % GC::TG;
+        int sl = L.lt / GC::GP, g = L.lt % GC::GP;
+        L.valid = (sl < GC::QPG) && (g < C::G);
+        L.slot = L.grp * GC::QPG + (sl < GC::QPG ? sl : 0);
+        thread_decode<C>(L.t, g < C::G ? g : 0);
+        L.t.q = L.slot;
+        B2_UNROLL
+        for (int e = 0; e < C::NV; e++) L.jij[e] = 0.0;
+        if (tid == 0) {
+            sm.bra.ABx = bpair.ABx; sm.bra.ABy = bpair.ABy; sm.bra.ABz = bpair.ABz;
+            sm.bra.i0 = bpair.i0; sm.bra.j0 = bpair.j0;
+            sm.bra.nprim = bpair.nprim; sm.bra.prim_off = bpair.prim_off;
+            sm.bra.same = bpair.same; sm.bra.idx = bx;
+            sm.nk = 0; sm.next = 0;
+        }
+    B2_END
+    B2_SYNC();
+
+    // ---- on-device screening: compact the surviving kets of this chunk
+    B2_ALL_THREADS(tid)
+        for (int kk = kbeg + tid; kk < kend; kk += GC::NT) {
+            const ShellPair& kp = P.ket_pairs[kk];
+            bool keep = keep_quartet(bpair.q, kp.q, bpair.ish, bpair.jsh, kp.ish, kp.jsh, P.dmc, P.nsh, P.tol,
+                                     P.vj != nullptr, P.vk != nullptr);
+            if (keep) {
+#if defined(__CUDA_ARCH__)
+                int pos = atomicAdd(&sm.nk, 1);
+#else
+                int pos = sm.nk++;
+#endif
+                sm.klist[pos] = kk;
+            }
+        }
+    B2_END
+    B2_SYNC();
+    const int nk = sm.nk;
+#if defined(__CUDA_ARCH__)
+    if (P.counters && threadIdx.x == 0) {
+        atomicAdd(&P.counters[0], (unsigned long long)nk);
+        atomicAdd(&P.counters[1], (unsigned long long)(kend - kbeg - nk));
+    }
+    group_proc<C>(P, sm, threadIdx.x / GC::TG, nk, bx, ctx);
+#else
+    if (P.counters) { P.counters[0] += nk; P.counters[1] += kend - kbeg - nk; }
+    for (int grp = 0; grp < GC::NG; grp++) group_proc<C>(P, sm, grp, nk, bx, ctxs);
+#endif
+
+    // ---- flush the register-resident J[ij] of the stationary bra pair
+    if (P.vj && P.n_dm_j == 1) {
+        B2_ALL_THREADS(tid)
+            LaneCtx<C>& L = B2_CTX(tid);
+            if (L.valid) {
+                const int b0 = L.t.p * C::NJP;
+                B2_UNROLL
+                for (int bb = 0; bb < C::NJP; bb++) {
+                    B2_UNROLL
+                    for (int a = 0; a < C::NI; a++) {
+                        double val = L.jij[bb * C::NI + a];
+                        if (val != 0.0) red_add(&P.vj[(size_t)(sm.bra.i0 + a) * P.n + (sm.bra.j0 + b0 + bb)], val);
+                    }
+                }
+            }
+        B2_END
     }
 #if !defined(__CUDA_ARCH__)
     delete[] ctxs;

@@ -17,53 +17,53 @@ template <int LI, int LJ, int LK, int LL>
 struct ClassCfg {
     static constexpr int NP = choose_np(ncart(LI), ncart(LJ));
     using C = QClass<LI, LJ, LK, LL, NP>;
-    static constexpr int NQ0 = (160 + C::G - 1) / C::G;
-    static constexpr int NQ = NQ0 < 1 ? 1 : (NQ0 > 64 ? 64 : NQ0);
-    static constexpr int NT = BlockCfg<C, NQ>::NT;
-    static constexpr int KCHUNK = (NQ * 8 > KCH_MAX) ? (KCH_MAX / NQ) * NQ : (NQ * 8 < 32 ? ((32 + NQ - 1) / NQ) * NQ : NQ * 8);
+    using GC = GroupCfg<C>;
+    static constexpr int NT = GC::NT;
+    // kets examined per CTA: enough batches per group to amortise the prologue and the J[ij] flush
+    static constexpr int KC0 = GC::NSLOT * 8;
+    static constexpr int KCHUNK = KC0 > KCH_MAX ? KCH_MAX : (KC0 < 64 ? 64 : KC0);
 };
 
 #ifndef B200JK_EMULATE
-template <class C, int NQ>
-__global__ void __launch_bounds__(BlockCfg<C, NQ>::NT) jk_class_kernel(const KParams P)
+template <class C>
+__global__ void __launch_bounds__(GroupCfg<C>::NT) jk_class_kernel(const KParams P)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
-    BlockSmem<C, NQ>& sm = *reinterpret_cast<BlockSmem<C, NQ>*>(smraw);
-    jk_block<C, NQ>(P, blockIdx.x, blockIdx.y, sm);
+    BlockSmem<C>& sm = *reinterpret_cast<BlockSmem<C>*>(smraw);
+    jk_block<C>(P, blockIdx.x, blockIdx.y, sm);
 }
 #endif
 
-template <int LI, int LJ, int LK, int LL>
-void launch_one(KParams P,
 #ifndef B200JK_EMULATE
-                cudaStream_t st
+typedef cudaStream_t b2_stream_t;
 #else
-                int st
+typedef int b2_stream_t;
 #endif
-)
+
+template <int LI, int LJ, int LK, int LL>
+void launch_one(KParams P, b2_stream_t st)
 {
     using Cfg = ClassCfg<LI, LJ, LK, LL>;
     using C = typename Cfg::C;
-    constexpr int NQ = Cfg::NQ;
     P.kchunk = Cfg::KCHUNK;
     int ny = (P.nket + P.kchunk - 1) / P.kchunk;
 #ifndef B200JK_EMULATE
     static bool configured = false;
-    size_t smem = sizeof(BlockSmem<C, NQ>);
+    size_t smem = sizeof(BlockSmem<C>);
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(jk_class_kernel<C, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(jk_class_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
         configured = true;
     }
     dim3 grid(P.nbra, ny);
-    jk_class_kernel<C, NQ><<<grid, Cfg::NT, smem, st>>>(P);
+    jk_class_kernel<C><<<grid, Cfg::NT, smem, st>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("jk_class_kernel launch: ") + cudaGetErrorString(e));
 #else
     (void)st;
-    BlockSmem<C, NQ>* sm = new BlockSmem<C, NQ>();
+    BlockSmem<C>* sm = new BlockSmem<C>();
     for (int bx = 0; bx < P.nbra; bx++)
-        for (int by = 0; by < ny; by++) jk_block<C, NQ>(P, bx, by, *sm);
+        for (int by = 0; by < ny; by++) jk_block<C>(P, bx, by, *sm);
     delete sm;
 #endif
 }
@@ -71,12 +71,6 @@ void launch_one(KParams P,
 // pair class id = l1*(l1+1)/2 + l2  (l1 >= l2)
 #define B2_PAIR_CASES(X) \
     X(0, 0, 0) X(1, 1, 0) X(2, 1, 1) X(3, 2, 0) X(4, 2, 1) X(5, 2, 2) X(6, 3, 0) X(7, 3, 1) X(8, 3, 2) X(9, 3, 3)
-
-#ifndef B200JK_EMULATE
-typedef cudaStream_t b2_stream_t;
-#else
-typedef int b2_stream_t;
-#endif
 
 template <int LI, int LJ>
 void launch_ket(int ck, const KParams& P, b2_stream_t st)

@@ -25,6 +25,10 @@
 
 namespace b200jk {
 
+#ifndef __CUDACC__
+inline double rsqrt(double x) { return 1.0 / sqrt(x); }
+#endif
+
 constexpr int LMAX = 4;  // g shells (aux); orbital classes are generated up to f
 constexpr int RYS_NMAX = 9, RYS_DEG = 13, RYS_NINT = 40;
 constexpr double RYS_H = 2.5, RYS_XMAX = 100.0;
@@ -93,7 +97,7 @@ struct PrimPair {  // 64 bytes, one per surviving primitive pair
     double p;             // a_i + a_j
     double Px, Py, Pz;    // Gaussian product centre
     double PAx, PAy, PAz; // P - A   (A = centre of the first shell of the pair)
-    double cc;            // c_i c_j exp(-a_i a_j |AB|^2 / p)
+    double cc;            // sqrt(2 pi^(5/2)) * c_i c_j exp(-a_i a_j |AB|^2 / p) / p
 };
 struct ShellPair {  // 48 bytes
     double ABx, ABy, ABz;  // A - B
@@ -175,15 +179,18 @@ B2_HD void slot_set_cd(SlotSmem<C>& s, double CDx, double CDy, double CDz)
 }
 
 // Phase A: Rys roots for primitive quartet (bp, kp).  Threads g, g+G, ... < NR of the slot.
+// PrimPair::cc carries sqrt(2 pi^2.5) c_i c_j K_ij / p, so the ERI prefactor is cc_b cc_k / sqrt(p+q).
 template <class C>
 B2_HD void phase_roots(SlotSmem<C>& s, int g, const PrimPair& bp, const PrimPair& kp, const RysTables& tb, double omega)
 {
     double p = bp.p, q = kp.p;
     double PQx = bp.Px - kp.Px, PQy = bp.Py - kp.Py, PQz = bp.Pz - kp.Pz;
     double pq = p + q;
-    double rho = p * q / pq;
+    double rs = rsqrt(pq);
+    double ipq = rs * rs;
+    double rho = p * q * ipq;
     double x = rho * (PQx * PQx + PQy * PQy + PQz * PQz);
-    double pref = PI_25_2 / (p * q * sqrt(pq)) * bp.cc * kp.cc;
+    double pref = bp.cc * kp.cc * rs;
     double theta = 1.0;
     if (omega > 0.0) {  // erf(omega r)/r: evaluate at x*theta, u*theta, w*sqrt(theta)
         theta = omega * omega / (omega * omega + rho);
@@ -201,6 +208,7 @@ B2_HD void phase_roots(SlotSmem<C>& s, int g, const PrimPair& bp, const PrimPair
         s.pc[2] = bp.PAx; s.pc[3] = bp.PAy; s.pc[4] = bp.PAz;
         s.pc[5] = kp.PAx; s.pc[6] = kp.PAy; s.pc[7] = kp.PAz;
         s.pc[8] = PQx; s.pc[9] = PQy; s.pc[10] = PQz;
+        s.pc[11] = ipq;
     }
 }
 
@@ -209,13 +217,14 @@ template <class C>
 B2_HD void phase_vrr(SlotSmem<C>& s, int g)
 {
     double p = s.pc[0], q = s.pc[1];
-    double ipq = 1.0 / (p + q);
+    double ipq = s.pc[11];
+    double hip = 0.5 / p, hiq = 0.5 / q;
     for (int task = g; task < 3 * C::NR; task += C::G) {
         int r = task / 3, x = task - 3 * r;
         double u = s.U[r];
         double b00 = 0.5 * u * ipq;
-        double b10 = (1.0 - u * q * ipq) * (0.5 / p);
-        double b01 = (1.0 - u * p * ipq) * (0.5 / q);
+        double b10 = (1.0 - u * q * ipq) * hip;
+        double b01 = (1.0 - u * p * ipq) * hiq;
         double c00 = s.pc[2 + x] - u * q * ipq * s.pc[8 + x];
         double c0p = s.pc[5 + x] + u * p * ipq * s.pc[8 + x];
         double* I = s.I[x][r];
@@ -323,7 +332,7 @@ inline void red_add(double* addr, double val) { *addr += val; }
 // dmj/dmk: [n_dm][n][n] Cartesian; dmj symmetric; dmk symmetric or antisymmetric.
 template <class C>
 B2_HD void phase_digest(const SlotSmem<C>& s, const ThreadCtx<C>& t, int i0, int j0, int n, int n_dm,
-                        const double* dmj, const double* dmk, double* vj, double* vk)
+                        const double* dmj, const double* dmk, double* vj, double* vk, double* jacc)
 {
     const double f = s.fac;
     const int kc = s.k0 + t.c, ld = s.l0 + t.d;
@@ -342,7 +351,8 @@ B2_HD void phase_digest(const SlotSmem<C>& s, const ThreadCtx<C>& t, int i0, int
                     double val = t.v[bb * C::NI + a];
                     size_t ij = (size_t)(i0 + a) * n + (j0 + b0 + bb);
                     jkl += val * D[ij];
-                    red_add(&J[ij], val * dkl);
+                    if (jacc) jacc[bb * C::NI + a] += val * dkl;  // stationary bra pair: flushed once per CTA
+                    else red_add(&J[ij], val * dkl);
                 }
             }
             red_add(&J[(size_t)kc * n + ld], 2.0 * f * jkl);
@@ -424,7 +434,7 @@ B2_HD double schwarz_pair(int la, int lb, const ShellPair& sp, const PrimPair* p
             double PA[3] = {bp.PAx, bp.PAy, bp.PAz}, QC[3] = {kq.PAx, kq.PAy, kq.PAz};
             double rho = p * q * ipq;
             double x = rho * (PQ[0] * PQ[0] + PQ[1] * PQ[1] + PQ[2] * PQ[2]);
-            double pref = PI_25_2 / (p * q * sqrt(pq)) * bp.cc * kq.cc;
+            double pref = bp.cc * kq.cc / sqrt(pq);
             double theta = 1.0;
             if (omega > 0.0) { theta = omega * omega / (omega * omega + rho); x *= theta; pref *= sqrt(theta); }
             for (int r = 0; r < nr; r++) {
