@@ -169,6 +169,9 @@ struct b200jk_handle_s {
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> cls_ev;
+    std::vector<cudaStream_t> side;      // class kernels are spread over side streams (small classes overlap)
+    std::vector<cudaEvent_t> side_ev;
+    cudaEvent_t ev_in = nullptr;
 #endif
     int profile = 0;
     double class_ms[NPC * NPC] = {0};
@@ -328,6 +331,10 @@ extern "C" int b200jk_create(b200jk_handle* out, const int32_t* atm, int natm, c
         h->stream = h->own_stream;
         CK(cudaEventCreate(&h->ev0));
         CK(cudaEventCreate(&h->ev1));
+        CK(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+        h->side.resize(8); h->side_ev.resize(8);
+        for (auto& s : h->side) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        for (auto& e : h->side_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 #endif
         (void)natm; (void)nenv;
         // ---- device shells: general contractions are split into segmented shells
@@ -454,6 +461,10 @@ extern "C" int b200jk_destroy(b200jk_handle h)
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (auto& s : h->side) cudaStreamDestroy(s);
+    for (auto& e : h->side_ev) cudaEventDestroy(e);
+    for (auto& e : h->cls_ev) cudaEventDestroy(e);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
 #endif
     delete h;
     return 0;
@@ -576,26 +587,48 @@ static int direct_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, 
 #ifndef B200JK_EMULATE
         CK(cudaEventRecord(h->ev0, st));
 #endif
+        // classes sorted by estimated work (largest first) and dealt round-robin onto the side streams
+        struct Job { int cb, ck; double cost; };
+        std::vector<Job> jobs;
         for (int cb = NPC - 1; cb >= 0; cb--)
             for (int ck = cb; ck >= 0; ck--) {
                 PairClass &B = h->pc[cb], &K = h->pc[ck];
                 if (B.kept.empty() || K.kept.empty()) continue;
-                P.bra_pairs = B.d_kept; P.nbra = (int)B.kept.size();
-                P.ket_pairs = K.d_kept; P.nket = (int)K.kept.size();
-                P.same_class = (cb == ck);
-#ifndef B200JK_EMULATE
-                if (h->profile) {
-                    if (h->cls_ev.empty()) { h->cls_ev.resize(2 * NPC * NPC); for (auto& e : h->cls_ev) CK(cudaEventCreate(&e)); }
-                    CK(cudaEventRecord(h->cls_ev[2 * (cb * NPC + ck)], st));
-                }
-#endif
-                launch_class(cb, ck, P, st);
-#ifndef B200JK_EMULATE
-                if (h->profile) CK(cudaEventRecord(h->cls_ev[2 * (cb * NPC + ck) + 1], st));
-#endif
-                launches++;
+                double nq = (double)B.kept.size() * K.kept.size() * (cb == ck ? 0.5 : 1.0);
+                double ncomp = (double)ncart(B.la) * ncart(B.lb) * ncart(K.la) * ncart(K.lb);
+                jobs.push_back({cb, ck, nq * (ncomp + 50.0) * ((B.la + B.lb + K.la + K.lb) / 2 + 1)});
             }
+        std::sort(jobs.begin(), jobs.end(), [](const Job& a, const Job& b) { return a.cost > b.cost; });
 #ifndef B200JK_EMULATE
+        CK(cudaEventRecord(h->ev_in, st));
+        for (auto& s : h->side) CK(cudaStreamWaitEvent(s, h->ev_in, 0));
+#endif
+        int jn = 0;
+        for (const Job& jb : jobs) {
+            int cb = jb.cb, ck = jb.ck;
+            PairClass &B = h->pc[cb], &K = h->pc[ck];
+            P.bra_pairs = B.d_kept; P.nbra = (int)B.kept.size();
+            P.ket_pairs = K.d_kept; P.nket = (int)K.kept.size();
+            P.same_class = (cb == ck);
+#ifndef B200JK_EMULATE
+            cudaStream_t ss = h->profile ? st : h->side[jn % h->side.size()];
+            if (h->profile) {
+                if (h->cls_ev.empty()) { h->cls_ev.resize(2 * NPC * NPC); for (auto& e : h->cls_ev) CK(cudaEventCreate(&e)); }
+                CK(cudaEventRecord(h->cls_ev[2 * (cb * NPC + ck)], ss));
+            }
+            launch_class(cb, ck, P, ss);
+            if (h->profile) CK(cudaEventRecord(h->cls_ev[2 * (cb * NPC + ck) + 1], ss));
+#else
+            launch_class(cb, ck, P, st);
+#endif
+            launches++;
+            jn++;
+        }
+#ifndef B200JK_EMULATE
+        for (size_t i = 0; i < h->side.size(); i++) {
+            CK(cudaEventRecord(h->side_ev[i], h->side[i]));
+            CK(cudaStreamWaitEvent(st, h->side_ev[i], 0));
+        }
         CK(cudaEventRecord(h->ev1, st));
 #endif
         // ---- back to the spherical basis with the final symmetrisation

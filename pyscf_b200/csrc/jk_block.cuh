@@ -35,7 +35,7 @@ constexpr int pow2ceil(int x) { int p = 1; while (p < x) p *= 2; return p; }
 template <class C>
 struct GroupCfg {
     static constexpr int G = C::G;
-    static constexpr int GP = G <= 32 ? pow2ceil(G) : ((G + 31) / 32) * 32;  // lanes reserved per quartet
+    static constexpr int GP = G <= 32 ? G : ((G + 31) / 32) * 32;              // lanes reserved per quartet
     static constexpr int GW = (GP + 31) / 32;                                // warps per group
     static constexpr int TG = GW * 32;                                       // threads per group
     static constexpr int QPG = GP <= 32 ? 32 / GP : 1;                       // quartets in flight per group

@@ -2,20 +2,44 @@
 // One kernel per angular-momentum class (bra pair class >= ket pair class), 55 classes for s..f.
 #pragma once
 #include <stdexcept>
-#include "jk_block.cuh"
+#include "jk_tpq.cuh"
 
 namespace b200jk {
 
-constexpr int choose_np(int ni, int nj)
+// lanes doing useful work when a quartet needs g threads (sub-warp packing or whole warps)
+constexpr int lane_eff_permille(int g) { return g <= 32 ? (32 / g) * g * 1000 / 32 : g * 1000 / (((g + 31) / 32) * 32); }
+
+// number of bra-component parts per quartet: register block between 15 and 40 doubles (thread-local
+// horizontal recurrences are amortised over the block), then maximise lane use
+constexpr int choose_np(int ni, int nj, int nkl)
 {
-    for (int np = 1; np <= nj; np++)
-        if (nj % np == 0 && ni * nj / np <= 30) return np;
-    return nj;
+    int nab = ni * nj;
+    int best = 0, best_eff = -1;
+    for (int np = 1; np <= nj; np++) {
+        if (nj % np != 0 || nab / np > 40) continue;
+        if (best && nab / np < 15) break;
+        if (nkl * np > 512) break;
+        int eff = lane_eff_permille(nkl * np);
+        if (eff > best_eff + 60) { best = np; best_eff = eff; }   // prefer fewer parts unless clearly better packed
+    }
+    return best ? best : nj;
+}
+
+// kets per CTA: at least one batch (`unit` kets in flight per CTA), at most `cap`, and small enough that
+// the class fills the 148 SMs several times over
+inline int pick_kchunk(int nbra, int nket, int unit, int cap)
+{
+    long want_ctas = 148L * 8;
+    long ny = (want_ctas + nbra - 1) / nbra;
+    long kc = (nket + ny - 1) / ny;
+    if (kc < unit) kc = unit;
+    if (kc > cap) kc = cap;
+    return (int)kc;
 }
 
 template <int LI, int LJ, int LK, int LL>
 struct ClassCfg {
-    static constexpr int NP = choose_np(ncart(LI), ncart(LJ));
+    static constexpr int NP = choose_np(ncart(LI), ncart(LJ), ncart(LK) * ncart(LL));
     using C = QClass<LI, LJ, LK, LL, NP>;
     using GC = GroupCfg<C>;
     static constexpr int NT = GC::NT;
@@ -25,6 +49,11 @@ struct ClassCfg {
 };
 
 #ifndef B200JK_EMULATE
+template <class C>
+__global__ void __launch_bounds__(TpqCfg<C>::NT) jk_tpq_kernel(const KParams P)
+{
+    tpq_block<C>(P, blockIdx.x, blockIdx.y);
+}
 template <class C>
 __global__ void __launch_bounds__(GroupCfg<C>::NT) jk_class_kernel(const KParams P)
 {
@@ -45,7 +74,23 @@ void launch_one(KParams P, b2_stream_t st)
 {
     using Cfg = ClassCfg<LI, LJ, LK, LL>;
     using C = typename Cfg::C;
-    P.kchunk = Cfg::KCHUNK;
+    if constexpr (TpqCfg<C>::eligible) {
+        // low angular momentum: one thread per quartet, registers only (jk_tpq.cuh)
+        P.kchunk = pick_kchunk(P.nbra, P.nket, TpqCfg<C>::NT, TpqCfg<C>::KCHUNK);
+        int ny = (P.nket + P.kchunk - 1) / P.kchunk;
+#ifndef B200JK_EMULATE
+        dim3 grid(P.nbra, ny);
+        jk_tpq_kernel<C><<<grid, TpqCfg<C>::NT, 0, st>>>(P);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) throw std::runtime_error(std::string("jk_tpq_kernel launch: ") + cudaGetErrorString(e));
+#else
+        (void)st;
+        for (int bx = 0; bx < P.nbra; bx++)
+            for (int by = 0; by < ny; by++) tpq_block<C>(P, bx, by);
+#endif
+        return;
+    }
+    P.kchunk = pick_kchunk(P.nbra, P.nket, Cfg::GC::NSLOT, KCH_MAX);
     int ny = (P.nket + P.kchunk - 1) / P.kchunk;
 #ifndef B200JK_EMULATE
     static bool configured = false;
