@@ -610,6 +610,7 @@ static int direct_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, 
             P.bra_pairs = B.d_kept; P.nbra = (int)B.kept.size();
             P.ket_pairs = K.d_kept; P.nket = (int)K.kept.size();
             P.same_class = (cb == ck);
+            P.bra_nprim_max = B.kept[0].nprim;  // kept lists are sorted by primitive count, largest first
 #ifndef B200JK_EMULATE
             cudaStream_t ss = h->profile ? st : h->side[jn % h->side.size()];
             if (h->profile) {

@@ -27,6 +27,7 @@ struct KParams {
     double* vj; double* vk;
     int n, n_dm_j, n_dm_k;
     int kchunk;
+    int bra_nprim_max;
     unsigned long long* counters;  // [0] quartets computed, [1] quartets screened out (may be null)
 };
 

@@ -52,7 +52,7 @@ struct ClassCfg {
 template <class C>
 __global__ void __launch_bounds__(TpqCfg<C>::NT) jk_tpq_kernel(const KParams P)
 {
-    tpq_block<C>(P, blockIdx.x, blockIdx.y);
+    tpq_block<C>(P, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 template <class C>
 __global__ void __launch_bounds__(GroupCfg<C>::NT) jk_class_kernel(const KParams P)
@@ -79,14 +79,15 @@ void launch_one(KParams P, b2_stream_t st)
         P.kchunk = pick_kchunk(P.nbra, P.nket, TpqCfg<C>::NT, TpqCfg<C>::KCHUNK);
         int ny = (P.nket + P.kchunk - 1) / P.kchunk;
 #ifndef B200JK_EMULATE
-        dim3 grid(P.nbra, ny);
+        dim3 grid(P.nbra, ny, (P.bra_nprim_max + TpqCfg<C>::PSLICE - 1) / TpqCfg<C>::PSLICE);
         jk_tpq_kernel<C><<<grid, TpqCfg<C>::NT, 0, st>>>(P);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) throw std::runtime_error(std::string("jk_tpq_kernel launch: ") + cudaGetErrorString(e));
 #else
         (void)st;
         for (int bx = 0; bx < P.nbra; bx++)
-            for (int by = 0; by < ny; by++) tpq_block<C>(P, bx, by);
+            for (int by = 0; by < ny; by++)
+                for (int bz = 0; bz * TpqCfg<C>::PSLICE < P.bra_nprim_max; bz++) tpq_block<C>(P, bx, by, bz);
 #endif
         return;
     }

@@ -122,16 +122,18 @@ struct QClass {
     static constexpr int NR = (LI + LJ + LK + LL) / 2 + 1;
     static constexpr int LB = LI + LJ, LT = LK + LL, NB1 = LB + 1, NT1 = LT + 1, ISZ = NB1 * NT1;
     static constexpr int NI1 = LI + 1, NJ1 = LJ + 1;
+    static constexpr int ISP = ISZ | 1;   // padded (odd) stride of one I(n,m) array: conflict-free across tasks
 };
 
 template <class C>
 struct SlotSmem {
-    double I[3][C::NR][C::ISZ];  // VRR output I[n*NT1+m]; z carries weight*prefactor
+    double I[3][C::NR][C::ISP];  // VRR output I[n*NT1+m]; z carries weight*prefactor
     double U[C::NR], W[C::NR];
     double pc[12];               // p, q, PA[3], QC[3], PQ[3], pad
     double ccd[3][C::LL + 1][C::LL + 1];  // binom(l,t) CD^(l-t)
     double fac;                  // symmetry factor (1, 1/2, 1/4, 1/8)
     int32_t kl, k0, l0, nprim_k, prim_off_k, active, pact, pad;
+    double pad_odd[((3 * C::NR * C::ISP + 2 * C::NR + 12 + 3 * (C::LL + 1) * (C::LL + 1) + 1 + 4) % 2 == 0) ? 1 : 2];  // odd slot stride
 };
 
 struct BraInfo {

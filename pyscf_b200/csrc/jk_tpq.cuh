@@ -18,6 +18,7 @@ struct TpqCfg {
     static constexpr bool eligible = (NOUT <= 36) && (C::NR <= 3) && (C::NP == 1);
     static constexpr int NT = 128;
     static constexpr int KCHUNK = 512;
+    static constexpr int PSLICE = 8;      // bra primitive pairs per CTA slice (blockIdx.z): bounds the serial work of a thread
     static constexpr int GI = C::LI + 1, GJ = C::LJ + 1, GK = C::LK + 1, GL = C::LL + 1;
     static constexpr int GSZ = GI * GJ * GK * GL;
 };
@@ -76,12 +77,12 @@ B2_HD void tpq_g2d(double c00, double c0p, double b00, double b10, double b01, d
 
 // all Cartesian integrals of one shell quartet: v[(d*NK + c)*NAB + b*NI + a]
 template <class C>
-B2_HD void tpq_eri(const KParams& P, const ShellPair& bp, const ShellPair& kp, double* v)
+B2_HD void tpq_eri(const KParams& P, const ShellPair& bp, const ShellPair& kp, int ib0, int ib1, double* v)
 {
     using T = TpqCfg<C>;
     B2_UNROLL
     for (int e = 0; e < T::NOUT; e++) v[e] = 0.0;
-    for (int ib = 0; ib < bp.nprim; ib++) {
+    for (int ib = ib0; ib < ib1; ib++) {
         const PrimPair b = P.prims[bp.prim_off + ib];
         for (int ik = 0; ik < kp.nprim; ik++) {
             const PrimPair k = P.prims[kp.prim_off + ik];
@@ -240,7 +241,7 @@ __device__ __forceinline__
 #else
 inline
 #endif
-void tpq_block(const KParams& P, int bx, int by)
+void tpq_block(const KParams& P, int bx, int by, int bz)
 {
     using T = TpqCfg<C>;
     const ShellPair bpair = P.bra_pairs[bx];
@@ -248,6 +249,9 @@ void tpq_block(const KParams& P, int bx, int by)
     const int kbeg = by * P.kchunk;
     const int kend = (kbeg + P.kchunk < kmax) ? kbeg + P.kchunk : kmax;
     if (kbeg >= kend) return;
+    const int ib0 = bz * T::PSLICE;
+    const int ib1 = (ib0 + T::PSLICE < bpair.nprim) ? ib0 + T::PSLICE : bpair.nprim;
+    if (ib0 >= ib1) return;
 #if defined(__CUDA_ARCH__)
     {
         const int tid = threadIdx.x;
@@ -265,16 +269,16 @@ void tpq_block(const KParams& P, int bx, int by)
             const ShellPair kp = P.ket_pairs[kk];
             if (!keep_quartet(bpair.q, kp.q, bpair.ish, bpair.jsh, kp.ish, kp.jsh, P.dmc, P.nsh, P.tol, P.vj != nullptr,
                               P.vk != nullptr)) {
-                skipped++;
+                if (bz == 0) skipped++;
                 continue;
             }
-            mine++;
+            if (bz == 0) mine++;
             double f = 1.0;
             if (bpair.same) f *= 0.5;
             if (kp.same) f *= 0.5;
             if (P.same_class && kk == bx) f *= 0.5;
             double v[T::NOUT];
-            tpq_eri<C>(P, bpair, kp, v);
+            tpq_eri<C>(P, bpair, kp, ib0, ib1, v);
             tpq_digest<C>(P, v, f, bpair.i0, bpair.j0, kp.i0, kp.j0, jij);
         }
 #if defined(__CUDA_ARCH__)
