@@ -71,6 +71,9 @@ int b200jk_df_build(b200jk_handle h, const int32_t* aux_atm, int aux_natm, const
 int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao, const double* occ_coeff, int nocc, int hermi,
                  double* vj, double* vk);
 int b200jk_df_naux(b200jk_handle h, int* naux);
+/* Rows [r0, r0+nr) of the device-resident tensor, reference layout cderi[naux, nao(nao+1)/2]
+ * (pyscf/df/incore.py:134-136; what DF.loop() yields, pyscf/df/df.py:214-242). */
+int b200jk_df_get_cderi(b200jk_handle h, double* out, int r0, int nr);
 
 /* Schwarz table q_cond[nbas,nbas] in the reference's (contracted, spherical-order) shell indexing. */
 int b200jk_get_q_cond(b200jk_handle h, double* q_cond, int nbas);

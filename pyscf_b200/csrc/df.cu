@@ -1,0 +1,662 @@
+// df.cu — density-fitting path of libb200jk.so.
+//
+//   b200jk_df_build : cderi[naux, nao(nao+1)/2] = L^-1 (P|ij)     <- incore.cholesky_eri, pyscf/df/incore.py:129-220
+//                     (P|Q), (ij|P) from the Rys kernels in df_block.cuh, Cholesky/TRSM on device
+//                     (eigendecomposition fallback with `lindep`, incore.py:150-158,263-270)
+//   b200jk_df_jk    : J = cderi^T (cderi . dmtril) ; K = sum_P (P|.i)(P|.i)^T  <- df_jk.get_jk, pyscf/df/df_jk.py:280-413
+// The tensor stays resident in HBM in the reference's own layout (row P, packed lower triangle mu>=nu).
+#include "host_common.hpp"
+#include "df_classes.cuh"
+
+#ifndef B200JK_EMULATE
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+#define CKB(call)                                                                                  \
+    do {                                                                                           \
+        cublasStatus_t s_ = (call);                                                                \
+        if (s_ != CUBLAS_STATUS_SUCCESS) {                                                         \
+            char buf_[256];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s failed: cublas status %d (%s:%d)", #call, (int)s_, __FILE__, __LINE__); \
+            throw std::runtime_error(buf_);                                                        \
+        }                                                                                          \
+    } while (0)
+#define CKS(call)                                                                                  \
+    do {                                                                                           \
+        cusolverStatus_t s_ = (call);                                                              \
+        if (s_ != CUSOLVER_STATUS_SUCCESS) {                                                       \
+            char buf_[256];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s failed: cusolver status %d (%s:%d)", #call, (int)s_, __FILE__, __LINE__); \
+            throw std::runtime_error(buf_);                                                        \
+        }                                                                                          \
+    } while (0)
+#endif
+
+using namespace b200jk;
+
+struct DFState {
+    std::vector<DevShell> ash;
+    int nash = 0, naux_cart = 0, naux_sph = 0, naux = 0;   // naux = rows of cderi (after lin.dep. removal)
+    std::vector<PrimPair> aprims;
+    PrimPair* d_aprims = nullptr;
+    std::vector<ShellPair> akets[LMAX + 1];
+    ShellPair* d_akets[LMAX + 1] = {nullptr};
+    int64_t* d_aket_off[LMAX + 1] = {nullptr};   // (P|Q): column offset of each aux shell = its Cartesian offset
+    int *d_acart_sh = nullptr, *d_acart_comp = nullptr, *d_asph_sh = nullptr, *d_asph_m = nullptr, *d_ash_l = nullptr,
+        *d_ash_cart = nullptr, *d_ash_sph = nullptr;
+    int64_t* d_ao_off[NPC] = {nullptr};
+    int64_t rowlen = 0;
+    int64_t* d_pairoff = nullptr;
+    long npair = 0;
+    double* d_cderi = nullptr;
+    double omega = 0.0;
+    // J/K workspaces
+    double *d_dmtril = nullptr, *d_rho = nullptr, *d_vjtril = nullptr, *d_A = nullptr, *d_Y = nullptr, *d_occ = nullptr,
+           *d_dm = nullptr, *d_vk = nullptr, *d_vj = nullptr;
+    size_t ws_rows = 0, ws_nocc = 0, ws_ndm = 0;
+#ifndef B200JK_EMULATE
+    cublasHandle_t cublas = nullptr;
+    cusolverDnHandle_t cusolver = nullptr;
+#endif
+};
+
+namespace {
+
+void df_free(DFState* d)
+{
+    if (!d) return;
+    dev_free(d->d_aprims);
+    for (int l = 0; l <= LMAX; l++) { dev_free(d->d_akets[l]); dev_free(d->d_aket_off[l]); }
+    dev_free(d->d_acart_sh); dev_free(d->d_acart_comp); dev_free(d->d_asph_sh); dev_free(d->d_asph_m);
+    dev_free(d->d_ash_l); dev_free(d->d_ash_cart); dev_free(d->d_ash_sph);
+    for (int c = 0; c < NPC; c++) dev_free(d->d_ao_off[c]);
+    dev_free(d->d_pairoff); dev_free(d->d_cderi);
+    dev_free(d->d_dmtril); dev_free(d->d_rho); dev_free(d->d_vjtril); dev_free(d->d_A); dev_free(d->d_Y); dev_free(d->d_occ);
+    dev_free(d->d_dm); dev_free(d->d_vk); dev_free(d->d_vj);
+#ifndef B200JK_EMULATE
+    if (d->cublas) cublasDestroy(d->cublas);
+    if (d->cusolver) cusolverDnDestroy(d->cusolver);
+#endif
+    delete d;
+}
+
+// ---- transform kernels -------------------------------------------------------------------------
+// aux index cart -> sph on whole rows: out[P_sph][col] = sum_c T[m,c] in[cart_off + c][col]
+struct AuxC2SFn {
+    const double* in; double* out; int64_t rowlen; int nrow_sph;
+    const int *sph_sh, *sph_m, *sh_l, *sh_cart, *c2s_off; const double* c2s;
+    B2_HD void operator()(long idx) const
+    {
+        int r = (int)(idx / rowlen);
+        int64_t col = idx - (int64_t)r * rowlen;
+        int s = sph_sh[r], l = sh_l[s], nc = (l + 1) * (l + 2) / 2;
+        const double* T = c2s + c2s_off[l] + sph_m[r] * nc;
+        double acc = 0.0;
+        for (int c = 0; c < nc; c++) {
+            double t = T[c];
+            if (t != 0.0) acc += t * in[(int64_t)(sh_cart[s] + c) * rowlen + col];
+        }
+        out[idx] = acc;
+    }
+};
+
+// AO pair cart blocks -> packed spherical lower triangle: out[r][mu(mu+1)/2+nu]
+struct PairC2SFn {
+    const double* in; double* out; int64_t rowlen; long npair; int nsh;
+    const int64_t* pairoff;
+    const int *sph_sh, *sph_m, *sh_l, *c2s_off; const double* c2s;
+    B2_HD void operator()(long idx) const
+    {
+        long r = idx / npair;
+        long t = idx - r * npair;
+        long mu = (long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while ((mu + 1) * (mu + 2) / 2 <= t) mu++;
+        while (mu * (mu + 1) / 2 > t) mu--;
+        long nu = t - mu * (mu + 1) / 2;
+        int sa = sph_sh[mu], sb = sph_sh[nu];
+        int la = sh_l[sa], lb = sh_l[sb];
+        int nca = (la + 1) * (la + 2) / 2, ncb = (lb + 1) * (lb + 2) / 2;
+        const double* Ta = c2s + c2s_off[la] + sph_m[mu] * nca;
+        const double* Tb = c2s + c2s_off[lb] + sph_m[nu] * ncb;
+        double acc = 0.0;
+        if (sa >= sb) {
+            int64_t off = pairoff[(int64_t)sa * nsh + sb];
+            if (off >= 0) {
+                const double* X = in + r * rowlen + off;   // X[b*nca + a]
+                for (int b = 0; b < ncb; b++) {
+                    double tb = Tb[b];
+                    if (tb == 0.0) continue;
+                    for (int a = 0; a < nca; a++) acc += Ta[a] * tb * X[b * nca + a];
+                }
+            }
+        } else {
+            int64_t off = pairoff[(int64_t)sb * nsh + sa];
+            if (off >= 0) {
+                const double* X = in + r * rowlen + off;   // block of (sb, sa): X[a*ncb + b]
+                for (int a = 0; a < nca; a++) {
+                    double ta = Ta[a];
+                    if (ta == 0.0) continue;
+                    for (int b = 0; b < ncb; b++) acc += ta * Tb[b] * X[a * ncb + b];
+                }
+            }
+        }
+        out[idx] = acc;
+    }
+};
+
+// dmtril[s][t] = D[mu,nu] + D[nu,mu] (diagonal once)      <- pyscf/df/df_jk.py:329-332
+struct DmTrilFn {
+    const double* dm; double* out; int nao; long npair;
+    B2_HD void operator()(long idx) const
+    {
+        long s = idx / npair, t = idx - s * npair;
+        long mu = (long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while ((mu + 1) * (mu + 2) / 2 <= t) mu++;
+        while (mu * (mu + 1) / 2 > t) mu--;
+        long nu = t - mu * (mu + 1) / 2;
+        const double* D = dm + s * (long)nao * nao;
+        out[idx] = (mu == nu) ? D[mu * nao + mu] : D[mu * nao + nu] + D[nu * nao + mu];
+    }
+};
+
+// unpack rows [r0, r0+nr) of the packed tensor into full symmetric nao x nao matrices
+struct UnpackFn {
+    const double* cderi; double* A; int nao; long npair; long r0;
+    B2_HD void operator()(long idx) const
+    {
+        long n2 = (long)nao * nao;
+        long r = idx / n2, e = idx - r * n2;
+        long i = e / nao, j = e - i * nao;
+        long mu = i >= j ? i : j, nu = i >= j ? j : i;
+        A[idx] = cderi[(r0 + r) * npair + mu * (mu + 1) / 2 + nu];
+    }
+};
+
+struct UnpackTrilFn {   // vj[s][i][j] from vjtril[s][t]
+    const double* tril; double* out; int nao; long npair;
+    B2_HD void operator()(long idx) const
+    {
+        long n2 = (long)nao * nao;
+        long s = idx / n2, e = idx - s * n2;
+        long i = e / nao, j = e - i * nao;
+        long mu = i >= j ? i : j, nu = i >= j ? j : i;
+        out[idx] = tril[s * npair + mu * (mu + 1) / 2 + nu];
+    }
+};
+
+#ifndef B200JK_EMULATE
+// rho[s][P] += sum_{t in segment} cderi[P][t] dmtril[s][t]  — grid (segments, rows, dms); coalesced, atomics on rho
+__global__ void __launch_bounds__(256) dfj_rho_kernel(const double* __restrict__ cderi, const double* __restrict__ dmtril,
+                                                      double* __restrict__ rho, long npair, long r0, int naux, long seglen)
+{
+    const long r = r0 + blockIdx.y;
+    const int s = blockIdx.z;
+    const long t0 = blockIdx.x * seglen;
+    const long t1 = (t0 + seglen < npair) ? t0 + seglen : npair;
+    const double* row = cderi + r * npair;
+    const double* d = dmtril + (long)s * npair;
+    double acc0 = 0.0, acc1 = 0.0;
+    long t = t0 + threadIdx.x;
+    for (; t + 256 < t1; t += 512) { acc0 += row[t] * d[t]; acc1 += row[t + 256] * d[t + 256]; }
+    for (; t < t1; t += 256) acc0 += row[t] * d[t];
+    double acc = acc0 + acc1;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 8; w++) tot += part[w];
+        atomicAdd(&rho[(long)s * naux + r], tot);
+    }
+}
+// vjtril[s][t] += sum_{P in block} rho[s][P] cderi[P][t]  — thread per column, rows just read stay in L2
+__global__ void __launch_bounds__(256) dfj_acc_kernel(const double* __restrict__ cderi, const double* __restrict__ rho,
+                                                      double* __restrict__ vjtril, long npair, long r0, int nr, int naux, int n_dm)
+{
+    long t = blockIdx.x * 256L + threadIdx.x;
+    if (t >= npair) return;
+    for (int s = 0; s < n_dm; s++) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const double* rh = rho + (long)s * naux + r0;
+        const double* col = cderi + r0 * npair + t;
+        int r = 0;
+        for (; r + 4 <= nr; r += 4) {
+            a0 += rh[r] * col[(long)r * npair];
+            a1 += rh[r + 1] * col[(long)(r + 1) * npair];
+            a2 += rh[r + 2] * col[(long)(r + 2) * npair];
+            a3 += rh[r + 3] * col[(long)(r + 3) * npair];
+        }
+        for (; r < nr; r++) a0 += rh[r] * col[(long)r * npair];
+        vjtril[(long)s * npair + t] += (a0 + a1) + (a2 + a3);
+    }
+}
+#endif
+
+void build_aux(b200jk_handle h, DFState* d, const int32_t* atm, const int32_t* bas, int nbas, const double* env)
+{
+    std::vector<DevShell> tmp;
+    int sph = 0;
+    for (int ib = 0; ib < nbas; ib++) {
+        const int32_t* b = bas + ib * BAS_SLOTS;
+        int l = b[ANG_OF], np = b[NPRIM_OF], nc = b[NCTR_OF];
+        if (l > LMAX) throw std::runtime_error("auxiliary angular momentum > g is not supported");
+        const double* r = env + atm[b[ATOM_OF] * ATM_SLOTS + PTR_COORD];
+        for (int c = 0; c < nc; c++) {
+            DevShell s;
+            s.l = l; s.ref_shell = ib; s.sph_off = sph + c * (2 * l + 1); s.cart_off = 0;
+            s.r[0] = r[0]; s.r[1] = r[1]; s.r[2] = r[2];
+            for (int p = 0; p < np; p++) {
+                double cf = env[b[PTR_COEFF] + c * np + p];
+                if (cf != 0.0) { s.e.push_back(env[b[PTR_EXP] + p]); s.c.push_back(cf); }
+            }
+            s.nprim = (int)s.e.size();
+            tmp.push_back(s);
+        }
+        sph += nc * (2 * l + 1);
+    }
+    d->naux_sph = sph;
+    std::stable_sort(tmp.begin(), tmp.end(), [](const DevShell& a, const DevShell& b) { return a.l < b.l; });
+    int co = 0;
+    for (auto& s : tmp) { s.cart_off = co; co += ncart(s.l); }
+    d->naux_cart = co;
+    d->ash = tmp;
+    d->nash = (int)tmp.size();
+    std::vector<int> cart_sh(co), cart_comp(co), sph_sh(sph), sph_m(sph), sh_l(d->nash), sh_cart(d->nash), sh_sph(d->nash);
+    std::vector<int64_t> koff[LMAX + 1];
+    for (int i = 0; i < d->nash; i++) {
+        const DevShell& s = d->ash[i];
+        sh_l[i] = s.l; sh_cart[i] = s.cart_off; sh_sph[i] = s.sph_off;
+        for (int a = 0; a < ncart(s.l); a++) { cart_sh[s.cart_off + a] = i; cart_comp[s.cart_off + a] = a; }
+        for (int m = 0; m < 2 * s.l + 1; m++) { sph_sh[s.sph_off + m] = i; sph_m[s.sph_off + m] = m; }
+        ShellPair sp{};
+        sp.ish = i; sp.jsh = -1; sp.i0 = s.cart_off; sp.j0 = 0; sp.same = 0;
+        sp.prim_off = (int)d->aprims.size(); sp.nprim = s.nprim;
+        for (int p = 0; p < s.nprim; p++) {
+            PrimPair pp;
+            pp.p = s.e[p]; pp.Px = s.r[0]; pp.Py = s.r[1]; pp.Pz = s.r[2];
+            pp.PAx = pp.PAy = pp.PAz = 0.0;
+            pp.cc = s.c[p] / s.e[p] * 5.914967172795612486;
+            d->aprims.push_back(pp);
+        }
+        d->akets[s.l].push_back(sp);
+        koff[s.l].push_back(s.cart_off);
+    }
+    d->d_aprims = upload(d->aprims);
+    for (int l = 0; l <= LMAX; l++) { d->d_akets[l] = upload(d->akets[l]); d->d_aket_off[l] = upload(koff[l]); }
+    d->d_acart_sh = upload(cart_sh); d->d_acart_comp = upload(cart_comp); d->d_asph_sh = upload(sph_sh); d->d_asph_m = upload(sph_m);
+    d->d_ash_l = upload(sh_l); d->d_ash_cart = upload(sh_cart); d->d_ash_sph = upload(sh_sph);
+    (void)h;
+}
+
+#ifdef B200JK_EMULATE
+// tiny dense helpers for the CPU emulation (tests only)
+void cpu_cholesky_lower(std::vector<double>& a, int n, bool& ok)
+{   // row-major symmetric -> L in lower triangle
+    ok = true;
+    for (int j = 0; j < n; j++) {
+        double s = a[(size_t)j * n + j];
+        for (int k = 0; k < j; k++) s -= a[(size_t)j * n + k] * a[(size_t)j * n + k];
+        if (!(s > 0)) { ok = false; return; }
+        double ljj = std::sqrt(s);
+        a[(size_t)j * n + j] = ljj;
+        for (int i = j + 1; i < n; i++) {
+            double t = a[(size_t)i * n + j];
+            for (int k = 0; k < j; k++) t -= a[(size_t)i * n + k] * a[(size_t)j * n + k];
+            a[(size_t)i * n + j] = t / ljj;
+        }
+    }
+}
+#endif
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200jk_df_build(b200jk_handle h, const int32_t* aux_atm, int aux_natm, const int32_t* aux_bas, int aux_nbas,
+                               const double* aux_env, int aux_nenv, double omega, double lindep)
+{
+    if (!h) return 1;
+    try {
+        (void)aux_natm; (void)aux_nenv;
+        if (omega < 0.0) throw std::runtime_error("short-range (omega<0) operator is not implemented on the device path");
+        if (h->df) { df_free(h->df); h->df = nullptr; }
+        DFState* d = new DFState();
+        h->df = d; h->df_free = df_free;
+        d->omega = omega;
+#ifndef B200JK_EMULATE
+        CK(cudaSetDevice(h->device));
+        cudaStream_t st = h->stream;
+        CKB(cublasCreate(&d->cublas));
+        CKS(cusolverDnCreate(&d->cusolver));
+#else
+        stream_t st = 0;
+#endif
+        build_aux(h, d, aux_atm, aux_bas, aux_nbas, aux_env);
+        const int nao = h->nsph, nsh = h->nsh;
+        d->npair = (long)nao * (nao + 1) / 2;
+
+        // ---- row layout of the Cartesian (ij| blocks and the (shell,shell) -> offset table
+        std::vector<int64_t> pairoff((size_t)nsh * nsh, -1);
+        int64_t off = 0;
+        for (int c = 0; c < NPC; c++) {
+            std::vector<int64_t> o;
+            for (auto& sp : h->pc[c].all) {
+                o.push_back(off);
+                pairoff[(size_t)sp.ish * nsh + sp.jsh] = off;
+                off += (int64_t)ncart(h->pc[c].la) * ncart(h->pc[c].lb);
+            }
+            d->d_ao_off[c] = upload(o);
+        }
+        d->rowlen = off;
+        d->d_pairoff = upload(pairoff);
+
+        // ---- (P|Q) in the Cartesian aux basis, then to spherical
+        const int nac = d->naux_cart, nas = d->naux_sph;
+        double* d_j2c_cart = (double*)dev_alloc((size_t)nac * nac * 8);
+        dev_zero(d_j2c_cart, (size_t)nac * nac * 8, st);
+        for (int lp = 0; lp <= LMAX; lp++)
+            for (int lq = 0; lq <= LMAX; lq++) {
+                if (d->akets[lp].empty() || d->akets[lq].empty()) continue;
+                J3cParams P{};
+                P.bra_pairs = d->d_akets[lp]; P.nbra = (int)d->akets[lp].size(); P.bra_out_off = d->d_aket_off[lp];
+                P.ket_shells = d->d_akets[lq]; P.nket = (int)d->akets[lq].size();
+                P.bra_prims = d->d_aprims; P.ket_prims = d->d_aprims;
+                P.tb = h->tb; P.omega = omega; P.out = d_j2c_cart; P.row_stride = nac;
+                int cb = (lp == 4) ? 10 : pair_class_id(lp, 0);
+                launch_j3c(cb, lq, P, st);
+            }
+        double* d_j2c = (double*)dev_alloc((size_t)nas * nas * 8);
+        Cart2SphFn c2 {d_j2c_cart, d_j2c, nas, nac, 0.0, 0, d->d_asph_sh, d->d_asph_m, d->d_ash_l, d->d_ash_cart, h->d_c2s_off, h->d_c2s};
+        launch_1d((long)nas * nas, c2, st);
+
+        // ---- metric decomposition: Cholesky, or eigendecomposition when it is not positive definite
+        //      (incore.py:150-158; _eig_decompose :263-270 keeps w > lindep)
+        bool use_chol = true;
+        std::vector<double> W;   // eig fallback: [naux_kept, naux] row-major
+        int nkeep = nas;
+#ifndef B200JK_EMULATE
+        {
+            int lwork = 0;
+            CKS(cusolverDnSetStream(d->cusolver, st));
+            CKB(cublasSetStream(d->cublas, st));
+            double* d_chol = (double*)dev_alloc((size_t)nas * nas * 8);
+            CK(cudaMemcpyAsync(d_chol, d_j2c, (size_t)nas * nas * 8, cudaMemcpyDeviceToDevice, st));
+            CKS(cusolverDnDpotrf_bufferSize(d->cusolver, CUBLAS_FILL_MODE_LOWER, nas, d_chol, nas, &lwork));
+            double* d_work = (double*)dev_alloc((size_t)lwork * 8);
+            int* d_info = (int*)dev_alloc(4);
+            CKS(cusolverDnDpotrf(d->cusolver, CUBLAS_FILL_MODE_LOWER, nas, d_chol, nas, d_work, lwork, d_info));
+            int info = 0;
+            d2h(&info, d_info, 4, st);
+            CK(cudaStreamSynchronize(st));
+            dev_free(d_work);
+            if (info != 0) {
+                use_chol = false;
+                // eigendecomposition on device
+                double* d_w = (double*)dev_alloc((size_t)nas * 8);
+                CK(cudaMemcpyAsync(d_chol, d_j2c, (size_t)nas * nas * 8, cudaMemcpyDeviceToDevice, st));
+                CKS(cusolverDnDsyevd_bufferSize(d->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nas, d_chol, nas, d_w, &lwork));
+                d_work = (double*)dev_alloc((size_t)lwork * 8);
+                CKS(cusolverDnDsyevd(d->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nas, d_chol, nas, d_w, d_work, lwork, d_info));
+                std::vector<double> w(nas), V((size_t)nas * nas);
+                d2h(w.data(), d_w, (size_t)nas * 8, st);
+                d2h(V.data(), d_chol, (size_t)nas * nas * 8, st);   // column-major eigenvectors: V[i + j*n]
+                CK(cudaStreamSynchronize(st));
+                dev_free(d_work); dev_free(d_w);
+                nkeep = 0;
+                for (int j = 0; j < nas; j++) if (w[j] > lindep) nkeep++;
+                W.assign((size_t)nkeep * nas, 0.0);
+                int k = 0;
+                for (int j = 0; j < nas; j++) {
+                    if (!(w[j] > lindep)) continue;
+                    double sc = 1.0 / std::sqrt(w[j]);
+                    for (int i = 0; i < nas; i++) W[(size_t)k * nas + i] = V[(size_t)i + (size_t)j * nas] * sc;
+                    k++;
+                }
+            }
+            dev_free(d_info);
+            // keep the factor in d_j2c (column-major lower == row-major upper of the same symmetric storage)
+            if (use_chol) CK(cudaMemcpyAsync(d_j2c, d_chol, (size_t)nas * nas * 8, cudaMemcpyDeviceToDevice, st));
+            dev_free(d_chol);
+        }
+#else
+        std::vector<double> j2c_h((size_t)nas * nas);
+        d2h(j2c_h.data(), d_j2c, (size_t)nas * nas * 8);
+        {
+            std::vector<double> Lm = j2c_h;
+            bool ok;
+            cpu_cholesky_lower(Lm, nas, ok);
+            if (!ok) throw std::runtime_error("emulation: metric not positive definite (eig fallback is GPU-only)");
+            j2c_h = Lm;
+        }
+        (void)lindep;
+#endif
+        d->naux = nkeep;
+
+        // ---- (ij|P): Cartesian rows -> spherical aux -> packed spherical pairs -> L^-1
+        const long npair = d->npair;
+        size_t cart_bytes = (size_t)nac * d->rowlen * 8, sphaux_bytes = (size_t)nas * d->rowlen * 8;
+        double* d_xc = (double*)dev_alloc(cart_bytes);
+        dev_zero(d_xc, cart_bytes, st);
+        for (int cb = 0; cb < NPC; cb++) {
+            if (h->pc[cb].all.empty()) continue;
+            for (int lk = 0; lk <= LMAX; lk++) {
+                if (d->akets[lk].empty()) continue;
+                J3cParams P{};
+                P.bra_pairs = h->pc[cb].d_all; P.nbra = (int)h->pc[cb].all.size(); P.bra_out_off = d->d_ao_off[cb];
+                P.ket_shells = d->d_akets[lk]; P.nket = (int)d->akets[lk].size();
+                P.bra_prims = h->d_prims; P.ket_prims = d->d_aprims;
+                P.tb = h->tb; P.omega = omega; P.out = d_xc; P.row_stride = d->rowlen;
+                launch_j3c(cb, lk, P, st);
+            }
+        }
+        double* d_xa = (double*)dev_alloc(sphaux_bytes);
+        AuxC2SFn a2 {d_xc, d_xa, d->rowlen, nas, d->d_asph_sh, d->d_asph_m, d->d_ash_l, d->d_ash_cart, h->d_c2s_off, h->d_c2s};
+        launch_1d((long)nas * d->rowlen, a2, st);
+#ifndef B200JK_EMULATE
+        CK(cudaStreamSynchronize(st));
+#endif
+        dev_free(d_xc);
+        double* d_j3c = (double*)dev_alloc((size_t)nas * npair * 8);
+        PairC2SFn p2 {d_xa, d_j3c, d->rowlen, npair, nsh, d->d_pairoff, h->d_sph_sh, h->d_sph_m, h->d_sh_l, h->d_c2s_off, h->d_c2s};
+        launch_1d((long)nas * npair, p2, st);
+#ifndef B200JK_EMULATE
+        CK(cudaStreamSynchronize(st));
+        dev_free(d_xa);
+        if (use_chol) {
+            // row-major j3c[naux, npair] == column-major [npair, naux]:  X * L^T = B  (right side, lower, transposed)
+            const double one = 1.0;
+            CKB(cublasDtrsm(d->cublas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)npair, nas,
+                            &one, d_j2c, nas, d_j3c, (int)npair));
+            d->d_cderi = d_j3c;
+        } else {
+            // cderi = W j3c ; column-major: C[npair, nkeep] = B[npair, nas] * W^T[nas, nkeep]
+            double* d_W = upload(W);
+            d->d_cderi = (double*)dev_alloc((size_t)nkeep * npair * 8);
+            const double one = 1.0, zero = 0.0;
+            CKB(cublasDgemm(d->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)npair, nkeep, nas, &one, d_j3c, (int)npair, d_W, nas, &zero,
+                            d->d_cderi, (int)npair));
+            CK(cudaStreamSynchronize(st));
+            dev_free(d_W); dev_free(d_j3c);
+        }
+        CK(cudaStreamSynchronize(st));
+#else
+        dev_free(d_xa);
+        {   // forward substitution row by row on the host (tests only)
+            double* X = d_j3c;
+            for (int i = 0; i < nas; i++) {
+                for (int k = 0; k < i; k++) {
+                    double lik = j2c_h[(size_t)i * nas + k];
+                    if (lik == 0.0) continue;
+                    for (long t = 0; t < npair; t++) X[(size_t)i * npair + t] -= lik * X[(size_t)k * npair + t];
+                }
+                double inv = 1.0 / j2c_h[(size_t)i * nas + i];
+                for (long t = 0; t < npair; t++) X[(size_t)i * npair + t] *= inv;
+            }
+            d->d_cderi = d_j3c;
+        }
+#endif
+        dev_free(d_j2c_cart); dev_free(d_j2c);
+    } catch (std::exception& e) { set_err(h, e.what()); return 2; }
+    return 0;
+}
+
+extern "C" int b200jk_df_naux(b200jk_handle h, int* naux)
+{
+    if (!h || !h->df || !naux) { set_err(h, "call b200jk_df_build first"); return 1; }
+    *naux = h->df->naux;
+    return 0;
+}
+
+// cderi rows [r0, r0+nr) copied to the host (tests, interchange with PySCF's with_df._cderi)
+extern "C" int b200jk_df_get_cderi(b200jk_handle h, double* out, int r0, int nr)
+{
+    if (!h || !h->df || !h->df->d_cderi) { set_err(h, "call b200jk_df_build first"); return 1; }
+    try {
+        DFState* d = h->df;
+        if (r0 < 0 || nr < 0 || r0 + nr > d->naux) throw std::runtime_error("row range out of bounds");
+        d2h(out, d->d_cderi + (size_t)r0 * d->npair, (size_t)nr * d->npair * 8);
+        dev_sync();
+    } catch (std::exception& e) { set_err(h, e.what()); return 2; }
+    return 0;
+}
+
+extern "C" int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao, const double* occ, int nocc, int hermi,
+                            double* vj, double* vk)
+{
+    if (!h) return 1;
+    try {
+        DFState* d = h->df;
+        if (!d || !d->d_cderi) throw std::runtime_error("call b200jk_df_build before b200jk_df_jk");
+        if (nao != h->nsph) throw std::runtime_error("nao does not match the basis of this handle");
+        if (n_dm < 1) throw std::runtime_error("n_dm < 1");
+        (void)hermi;
+        auto t0 = std::chrono::steady_clock::now();
+        const long npair = d->npair, n2 = (long)nao * nao;
+        const int naux = d->naux;
+#ifndef B200JK_EMULATE
+        CK(cudaSetDevice(h->device));
+        cudaStream_t st = h->stream;
+        CKB(cublasSetStream(d->cublas, st));
+#else
+        stream_t st = 0;
+#endif
+        // rows per block: the block is read twice (rho, then J) and should stay in L2; K unpacks it to nao^2
+        int rb = (int)std::max<long>(1, std::min<long>(naux, (40L << 20) / (npair * 8)));
+        int kb = (int)std::max<long>(1, std::min<long>(naux, (512L << 20) / (n2 * 8)));
+        if ((size_t)n_dm > d->ws_ndm) {
+            for (double** p : {&d->d_dmtril, &d->d_rho, &d->d_vjtril, &d->d_dm, &d->d_vk, &d->d_vj}) { dev_free(*p); *p = nullptr; }
+            d->d_dmtril = (double*)dev_alloc((size_t)n_dm * npair * 8);
+            d->d_vjtril = (double*)dev_alloc((size_t)n_dm * npair * 8);
+            d->d_rho = (double*)dev_alloc((size_t)n_dm * naux * 8);
+            d->d_dm = (double*)dev_alloc((size_t)n_dm * n2 * 8);
+            d->d_vk = (double*)dev_alloc((size_t)n_dm * n2 * 8);
+            d->d_vj = (double*)dev_alloc((size_t)n_dm * n2 * 8);
+            d->ws_ndm = n_dm;
+        }
+        h2d(d->d_dm, dm, (size_t)n_dm * n2 * 8, st);
+        uint64_t launches = 0;
+#ifndef B200JK_EMULATE
+        CK(cudaEventRecord(h->ev0, st));
+#endif
+        if (vj) {
+            DmTrilFn tf{d->d_dm, d->d_dmtril, nao, npair};
+            launch_1d((long)n_dm * npair, tf, st); launches++;
+            dev_zero(d->d_vjtril, (size_t)n_dm * npair * 8, st);
+#ifndef B200JK_EMULATE
+            dev_zero(d->d_rho, (size_t)n_dm * naux * 8, st);
+            const long seglen = 16384;   // 128 KiB of a row per CTA
+            const unsigned nseg = (unsigned)((npair + seglen - 1) / seglen);
+            // two streaming passes over the tensor (rho, then J): 2 launches, both HBM-bound
+            (void)rb;
+            for (int r0 = 0; r0 < naux; r0 += 32768) {
+                int nr = std::min(32768, naux - r0);
+                dfj_rho_kernel<<<dim3(nseg, nr, n_dm), 256, 0, st>>>(d->d_cderi, d->d_dmtril, d->d_rho, npair, r0, naux, seglen);
+                launches++;
+            }
+            dfj_acc_kernel<<<(unsigned)((npair + 255) / 256), 256, 0, st>>>(d->d_cderi, d->d_rho, d->d_vjtril, npair, 0, naux, naux, n_dm);
+            launches++;
+            CK(cudaGetLastError());
+#else
+            for (int s = 0; s < n_dm; s++)
+                for (int r = 0; r < naux; r++) {
+                    double acc = 0;
+                    for (long t = 0; t < npair; t++) acc += d->d_cderi[(size_t)r * npair + t] * d->d_dmtril[(size_t)s * npair + t];
+                    for (long t = 0; t < npair; t++) d->d_vjtril[(size_t)s * npair + t] += acc * d->d_cderi[(size_t)r * npair + t];
+                }
+#endif
+            UnpackTrilFn uf{d->d_vjtril, d->d_vj, nao, npair};
+            launch_1d((long)n_dm * n2, uf, st); launches++;
+            d2h(vj, d->d_vj, (size_t)n_dm * n2 * 8, st);
+        }
+        if (vk) {
+            bool use_occ = (occ != nullptr && nocc > 0);
+            int ncol = use_occ ? nocc : nao;
+            if ((size_t)kb > d->ws_rows || (size_t)ncol > d->ws_nocc) {
+                dev_free(d->d_A); dev_free(d->d_Y); dev_free(d->d_occ);
+                d->d_A = (double*)dev_alloc((size_t)kb * n2 * 8);
+                d->d_Y = (double*)dev_alloc((size_t)kb * ncol * nao * 8);
+                d->d_occ = (double*)dev_alloc((size_t)n_dm * nao * ncol * 8);
+                d->ws_rows = kb; d->ws_nocc = ncol;
+            }
+            if (use_occ) h2d(d->d_occ, occ, (size_t)n_dm * nao * nocc * 8, st);
+            dev_zero(d->d_vk, (size_t)n_dm * n2 * 8, st);
+            for (int r0 = 0; r0 < naux; r0 += kb) {
+                int nr = std::min(kb, naux - r0);
+                UnpackFn up{d->d_cderi, d->d_A, nao, npair, r0};
+                launch_1d((long)nr * n2, up, st); launches++;
+                for (int s = 0; s < n_dm; s++) {
+#ifndef B200JK_EMULATE
+                    const double one = 1.0, zero = 0.0;
+                    if (use_occ) {
+                        // Y_P (col-major [nao, nocc]) = A_P * Ctilde ; buffers: occ row-major [nao,nocc] == col-major [nocc,nao]
+                        CKB(cublasDgemmStridedBatched(d->cublas, CUBLAS_OP_N, CUBLAS_OP_T, nao, nocc, nao, &one, d->d_A, nao, n2,
+                                                      d->d_occ + (size_t)s * nao * nocc, nocc, 0, &zero, d->d_Y, nao,
+                                                      (long long)nao * nocc, nr));
+                        // K += Z Z^T, Z = [nao, nr*nocc]
+                        CKB(cublasDgemm(d->cublas, CUBLAS_OP_N, CUBLAS_OP_T, nao, nao, nr * nocc, &one, d->d_Y, nao, d->d_Y, nao, &one,
+                                        d->d_vk + (size_t)s * n2, nao));
+                    } else {
+                        // general dm: T_P = A_P * Dbuf (col-major view), K += sum_P T_P * A_P
+                        CKB(cublasDgemmStridedBatched(d->cublas, CUBLAS_OP_N, CUBLAS_OP_N, nao, nao, nao, &one, d->d_A, nao, n2,
+                                                      d->d_dm + (size_t)s * n2, nao, 0, &zero, d->d_Y, nao, n2, nr));
+                        CKB(cublasDgemm(d->cublas, CUBLAS_OP_N, CUBLAS_OP_T, nao, nao, nr * nao, &one, d->d_Y, nao, d->d_A, nao, &one,
+                                        d->d_vk + (size_t)s * n2, nao));
+                    }
+                    launches += 2;
+#else
+                    // K[i,l] += sum_P sum_jk A_P[i,j] D[j,k] A_P[k,l]   (tests only, O(N^4))
+                    const double* D = d->d_dm + (size_t)s * n2;
+                    double* K = d->d_vk + (size_t)s * n2;
+                    std::vector<double> T(n2);
+                    for (int r = 0; r < nr; r++) {
+                        const double* A = d->d_A + (size_t)r * n2;
+                        for (int i = 0; i < nao; i++)
+                            for (int k = 0; k < nao; k++) {
+                                double acc = 0;
+                                for (int j = 0; j < nao; j++) acc += A[(size_t)i * nao + j] * D[(size_t)j * nao + k];
+                                T[(size_t)i * nao + k] = acc;
+                            }
+                        for (int i = 0; i < nao; i++)
+                            for (int l = 0; l < nao; l++) {
+                                double acc = 0;
+                                for (int k = 0; k < nao; k++) acc += T[(size_t)i * nao + k] * A[(size_t)k * nao + l];
+                                K[(size_t)i * nao + l] += acc;
+                            }
+                    }
+#endif
+                }
+            }
+            d2h(vk, d->d_vk, (size_t)n_dm * n2 * 8, st);
+        }
+#ifndef B200JK_EMULATE
+        CK(cudaEventRecord(h->ev1, st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->stats.ms_kernels = ms;
+#endif
+        auto t1 = std::chrono::steady_clock::now();
+        h->stats.ms_total = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        h->stats.kernel_launches = launches;
+    } catch (std::exception& e) { set_err(h, e.what()); return 2; }
+    return 0;
+}

@@ -1,0 +1,94 @@
+"""Density-fitting path: emulated (CPU) and GPU parity against the oracle's restatement of
+incore.cholesky_eri / df_jk.get_jk and the reference fingerprints (pyscf/df/test/test_df_jk.py:144-156)."""
+import numpy as np
+import pytest
+
+from pyscf_b200 import gto
+from pyscf_b200.df import DF, TaggedDM
+from pyscf_b200.gto.mole import make_auxmol, geometry
+from oracle import oracle as O
+
+H2O = 'O 0 0 0; H 0 -0.757 0.587; H 0 0.757 0.587'
+
+
+def _check_h2o(libpath):
+    mol = gto.M(atom=H2O, basis='cc-pvdz')
+    d = DF(mol, 'weigend', libpath=libpath).build()
+    ref, nao = O.cholesky_eri(mol, make_auxmol(mol, 'weigend'))
+    assert d.get_naoaux() == ref.shape[0]
+    assert abs(d._cderi - ref).max() < 1e-10
+    np.random.seed(1)
+    dms = np.random.random((2, nao, nao))
+    vj, vk = d.get_jk(dms, hermi=0)
+    assert abs(O.fp(vj) - (-194.15910890730066)) < 1e-9   # test_df_jk.py:151-152
+    assert abs(O.fp(vk) - (-46.365071587653517)) < 1e-9
+    rj, rk = O.df_get_jk(ref, nao, dms)
+    assert abs(vj - rj).max() < 1e-10 and abs(vk - rk).max() < 1e-10
+    # mo_coeff fast path == general path (df_jk.py:339-357 vs :382-408)
+    c = np.linalg.qr(np.random.random((nao, 5)))[0]
+    occ = np.full(5, 2.0)
+    dm = TaggedDM((c * occ).dot(c.T), mo_coeff=c, mo_occ=occ)
+    vj1, vk1 = d.get_jk(dm, hermi=1)
+    vj2, vk2 = d.get_jk(np.asarray(dm), hermi=1)
+    assert abs(vj1 - vj2).max() < 1e-10 and abs(vk1 - vk2).max() < 1e-10
+    return d
+
+
+def test_df_emulated(emu_lib):
+    _check_h2o(emu_lib)
+
+
+def test_df_emulated_long_range(emu_lib):
+    mol = gto.M(atom=H2O, basis='6-31g')
+    d = DF(mol, 'weigend', libpath=emu_lib)
+    d.omega = 0.3
+    d.build()
+    ref, nao = O.cholesky_eri(mol, make_auxmol(mol, 'weigend'), omega=0.3)
+    # the long-range metric is numerically singular (smallest eigenvalue ~1e-15), so cderi itself is not
+    # unique to rounding (SURVEY.md §7 hard part 6; the reference pins RSH-DF to 1e-3, df/test/test_df.py:101-117):
+    # compare the J/K it produces
+    np.random.seed(0)
+    dm = np.random.random((nao, nao))
+    dm = dm + dm.T
+    vj, vk = d.get_jk(dm)
+    rj, rk = O.df_get_jk(ref, nao, dm)
+    assert abs(vj - rj).max() < 1e-8 and abs(vk - rk).max() < 1e-8
+
+
+@pytest.mark.gpu
+def test_df_gpu_h2o():
+    _check_h2o(None)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('basis,aux', [('cc-pvtz', 'cc-pvtz-jkfit'), ('def2-tzvp', 'def2-tzvp-jkfit')])
+def test_df_gpu_high_l(basis, aux):
+    # f orbital shells and g auxiliary shells
+    mol = gto.M(atom=H2O, basis=basis)
+    d = DF(mol, aux).build()
+    ref, nao = O.cholesky_eri(mol, make_auxmol(mol, aux))
+    assert abs(d._cderi - ref).max() < 1e-9
+    np.random.seed(2)
+    dm = np.random.random((nao, nao))
+    dm = dm + dm.T
+    vj, vk = d.get_jk(dm)
+    rj, rk = O.df_get_jk(ref, nao, dm)
+    assert abs(vj - rj).max() < 1e-9 and abs(vk - rk).max() < 1e-9
+
+
+@pytest.mark.gpu
+def test_df_gpu_benzene_properties():
+    mol = gto.M(atom=geometry('benzene'), basis='def2-svp')
+    d = DF(mol).build()          # def2-svp-jkfit via DEFAULT_AUXBASIS
+    nao = mol.nao
+    rng = np.random.RandomState(0)
+    a = rng.random_sample((nao, nao)); a = a + a.T
+    b = rng.random_sample((nao, nao)); b = b + b.T
+    (ja, jb), (ka, kb) = d.get_jk(np.array([a, b]))
+    jab, kab = d.get_jk(0.5 * a - 2 * b)
+    assert abs(jab - (0.5 * ja - 2 * jb)).max() < 1e-9 and abs(kab - (0.5 * ka - 2 * kb)).max() < 1e-9
+    assert abs(ja - ja.T).max() < 1e-10 and abs(ka - ka.T).max() < 1e-10
+    # DF approximates the exact 4-center J/K from above in the Coulomb metric: compare loosely
+    from pyscf_b200.jk import VHFOpt
+    ej, ek = VHFOpt(mol).get_jk(a)
+    assert abs(ja - ej).max() < 0.1 and abs(ka - ek).max() < 0.1   # fitting error of def2-svp-jkfit, elements O(100)
