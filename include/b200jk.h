@@ -88,6 +88,9 @@ int b200jk_fp64_peak(b200jk_handle h, double* tflops);
  * ms[100]: entry [cb*10+ck], pair class id = l1*(l1+1)/2+l2 (ss,ps,pp,ds,dp,dd,fs,fp,fd,ff). */
 int b200jk_set_profile(b200jk_handle h, int on);
 int b200jk_get_class_times(b200jk_handle h, double* ms, int n);
+/* Self-test of the tcgen05 int8-slice GEMM used by DF-K: C[M,N] = A[M,K] B[N,K]^T with `ns` 7-bit slices. */
+int b200jk_i8gemm_test(b200jk_handle h, int M, int N, int K, const double* A, const double* B, double* C, int ns,
+                       int symmetric);
 int b200jk_get_stats(b200jk_handle h, b200jk_stats* out);
 const char* b200jk_last_error(b200jk_handle h);
 const char* b200jk_version(void);

@@ -1,0 +1,18 @@
+// i8gemm_host.hpp — host interface of the tcgen05 int8-slice GEMM (i8gemm.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+namespace b200jk {
+namespace i8g {
+struct SliceStack {      // [ns][Rp][Kp] int8 slices + per-row exponents, device resident
+    int8_t* q = nullptr; int* E = nullptr;
+    int R = 0, K = 0, Rp = 0, Kp = 0, ns = 0;
+    size_t cap = 0; int ecap = 0;
+    void alloc(int rows, int k, int ns);
+    void release();
+};
+void split_rows(SliceStack& S, const double* X, long ldx, int rows, int k, int ns, cudaStream_t st);
+// C[m*ldc + n] (or the transposed scatter when inner>0, see GemmParams) += A B^T
+void gemm(const SliceStack& A, const SliceStack& B, double* C, long ldc, int inner, bool symmetric, cudaStream_t st);
+}  // namespace i8g
+}  // namespace b200jk
