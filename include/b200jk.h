@@ -71,6 +71,9 @@ int b200jk_df_build(b200jk_handle h, const int32_t* aux_atm, int aux_natm, const
 int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao, const double* occ_coeff, int nocc, int hermi,
                  double* vj, double* vk);
 int b200jk_df_naux(b200jk_handle h, int* naux);
+/* K-build engine for the occupied-orbital path: mode 1 (default) = tcgen05 int8-slice GEMMs (i8gemm.cuh) with
+ * `nslices` 7-bit slices (7 -> ~1e-11 relative), mode 0 = cuBLAS DGEMM on the FP64 pipe (kept as yardstick). */
+int b200jk_df_set_kmode(b200jk_handle h, int mode, int nslices);
 /* Rows [r0, r0+nr) of the device-resident tensor, reference layout cderi[naux, nao(nao+1)/2]
  * (pyscf/df/incore.py:134-136; what DF.loop() yields, pyscf/df/df.py:214-242). */
 int b200jk_df_get_cderi(b200jk_handle h, double* out, int r0, int nr);

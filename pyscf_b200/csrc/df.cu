@@ -11,6 +11,7 @@
 #ifndef B200JK_EMULATE
 #include <cublas_v2.h>
 #include <cusolverDn.h>
+#include "i8gemm_host.hpp"
 #define CKB(call)                                                                                  \
     do {                                                                                           \
         cublasStatus_t s_ = (call);                                                                \
@@ -53,9 +54,14 @@ struct DFState {
     double *d_dmtril = nullptr, *d_rho = nullptr, *d_vjtril = nullptr, *d_A = nullptr, *d_Y = nullptr, *d_occ = nullptr,
            *d_dm = nullptr, *d_vk = nullptr, *d_vj = nullptr;
     size_t ws_rows = 0, ws_nocc = 0, ws_ndm = 0;
+    int k_mode = 1;      // 0: cuBLAS DGEMM (FP64 pipe), 1: tcgen05 int8 slices (i8gemm.cuh)
+    int k_slices = 7;
+    double* d_Y2 = nullptr; double* d_occT = nullptr; size_t y2_cap = 0, occT_cap = 0;
 #ifndef B200JK_EMULATE
     cublasHandle_t cublas = nullptr;
     cusolverDnHandle_t cusolver = nullptr;
+    i8g::SliceStack SA, SC, SY;
+    bool sa_persistent = false; int sa_ns = 0;   // slices of the whole unpacked tensor kept resident (memory permitting)
 #endif
 };
 
@@ -71,8 +77,9 @@ void df_free(DFState* d)
     for (int c = 0; c < NPC; c++) dev_free(d->d_ao_off[c]);
     dev_free(d->d_pairoff); dev_free(d->d_cderi);
     dev_free(d->d_dmtril); dev_free(d->d_rho); dev_free(d->d_vjtril); dev_free(d->d_A); dev_free(d->d_Y); dev_free(d->d_occ);
-    dev_free(d->d_dm); dev_free(d->d_vk); dev_free(d->d_vj);
+    dev_free(d->d_dm); dev_free(d->d_vk); dev_free(d->d_vj); dev_free(d->d_Y2); dev_free(d->d_occT);
 #ifndef B200JK_EMULATE
+    d->SA.release(); d->SC.release(); d->SY.release();
     if (d->cublas) cublasDestroy(d->cublas);
     if (d->cusolver) cusolverDnDestroy(d->cusolver);
 #endif
@@ -169,6 +176,15 @@ struct UnpackFn {
         long mu = i >= j ? i : j, nu = i >= j ? j : i;
         A[idx] = cderi[(r0 + r) * npair + mu * (mu + 1) / 2 + nu];
     }
+};
+
+struct TransposeFn {   // out[c][r] = in[r][c]
+    const double* in; double* out; int rows, cols;
+    B2_HD void operator()(long idx) const { long r = idx / cols, c = idx - r * cols; out[c * (long)rows + r] = in[idx]; }
+};
+struct MirrorUpperFn {  // fill the strict lower triangle from the upper one
+    double* a; int n;
+    B2_HD void operator()(long idx) const { long i = idx / n, j = idx - i * n; if (j < i) a[idx] = a[j * (long)n + i]; }
 };
 
 struct UnpackTrilFn {   // vj[s][i][j] from vjtril[s][t]
@@ -541,7 +557,7 @@ extern "C" int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao
 #endif
         // rows per block: the block is read twice (rho, then J) and should stay in L2; K unpacks it to nao^2
         int rb = (int)std::max<long>(1, std::min<long>(naux, (40L << 20) / (npair * 8)));
-        int kb = (int)std::max<long>(1, std::min<long>(naux, (512L << 20) / (n2 * 8)));
+        int kb = (int)std::max<long>(1, std::min<long>(naux, (2048L << 20) / (n2 * 8)));
         if ((size_t)n_dm > d->ws_ndm) {
             for (double** p : {&d->d_dmtril, &d->d_rho, &d->d_vjtril, &d->d_dm, &d->d_vk, &d->d_vj}) { dev_free(*p); *p = nullptr; }
             d->d_dmtril = (double*)dev_alloc((size_t)n_dm * npair * 8);
@@ -599,13 +615,86 @@ extern "C" int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao
             }
             if (use_occ) h2d(d->d_occ, occ, (size_t)n_dm * nao * nocc * 8, st);
             dev_zero(d->d_vk, (size_t)n_dm * n2 * 8, st);
+#ifndef B200JK_EMULATE
+            const bool tc = use_occ && d->k_mode == 1;
+            if (tc) {
+                // int32 accumulation bound: pairs(<=ns) * K * 64*64 < 2^31
+                int kmax = (int)((1L << 19) / d->k_slices);
+                kb = std::max(1, std::min(kb, kmax / nocc));
+                if ((size_t)kb * nocc * nao > d->y2_cap) { dev_free(d->d_Y2); d->y2_cap = (size_t)kb * nocc * nao; d->d_Y2 = (double*)dev_alloc(d->y2_cap * 8); }
+                if ((size_t)nocc * nao > d->occT_cap) { dev_free(d->d_occT); d->occT_cap = (size_t)nocc * nao; d->d_occT = (double*)dev_alloc(d->occT_cap * 8); }
+            }
+#endif
+#ifndef B200JK_EMULATE
+            if (tc && !(d->sa_persistent && d->sa_ns == d->k_slices)) {
+                // slice the whole unpacked tensor once and keep it (7 B per element) when it fits comfortably
+                size_t freeb = 0, totb = 0;
+                CK(cudaMemGetInfo(&freeb, &totb));
+                size_t rows_tot = (size_t)naux * nao, rp = ((rows_tot + 255) / 256) * 256, kp = ((size_t)nao + 127) / 128 * 128;
+                size_t need = (size_t)d->k_slices * rp * kp;
+                d->sa_persistent = false;
+                if (need < freeb / 2 && rows_tot < (1u << 31)) {
+                    d->SA.alloc((int)rows_tot, nao, d->k_slices);
+                    CK(cudaMemsetAsync(d->SA.q, 0, need, st));
+                    CK(cudaMemsetAsync(d->SA.E, 0, rp * 4, st));
+                    for (int r0 = 0; r0 < naux; r0 += kb) {
+                        int nr = std::min(kb, naux - r0);
+                        UnpackFn up{d->d_cderi, d->d_A, nao, npair, r0};
+                        launch_1d((long)nr * n2, up, st);
+                        i8g::split_rows_into(d->SA, r0 * nao, d->d_A, nao, nr * nao, st);
+                    }
+                    d->sa_persistent = true; d->sa_ns = d->k_slices;
+                }
+            }
+#endif
             for (int r0 = 0; r0 < naux; r0 += kb) {
                 int nr = std::min(kb, naux - r0);
+#ifndef B200JK_EMULATE
+                if (!(tc && d->sa_persistent)) {
+                    UnpackFn up{d->d_cderi, d->d_A, nao, npair, r0};
+                    launch_1d((long)nr * n2, up, st); launches++;
+                    if (tc) { i8g::split_rows(d->SA, d->d_A, nao, nr * nao, nao, d->k_slices, st); launches++; }
+                }
+#else
                 UnpackFn up{d->d_cderi, d->d_A, nao, npair, r0};
                 launch_1d((long)nr * n2, up, st); launches++;
+#endif
                 for (int s = 0; s < n_dm; s++) {
 #ifndef B200JK_EMULATE
                     const double one = 1.0, zero = 0.0;
+                    if (tc) {
+                        // tcgen05 path: Y2[nu][(P,i)] = sum_mu A_P[nu,mu] Ct[i,mu] ; K += Y2 Y2^T (upper triangle)
+                        if (r0 == 0 || n_dm > 1) {
+                            TransposeFn tr{d->d_occ + (size_t)s * nao * nocc, d->d_occT, nao, nocc};
+                            launch_1d((long)nao * nocc, tr, st);
+                            i8g::split_rows(d->SC, d->d_occT, nao, nocc, nao, d->k_slices, st); launches += 2;
+                        }
+                        static const bool prof = getenv("B200JK_DF_PROFILE") != nullptr;
+                        static double tacc[5];
+                        auto tick = [&](int i) {
+                            if (!prof) return;
+                            static std::chrono::steady_clock::time_point last;
+                            CK(cudaStreamSynchronize(st));
+                            auto now = std::chrono::steady_clock::now();
+                            if (i >= 0) tacc[i] += std::chrono::duration<double, std::milli>(now - last).count();
+                            last = now;
+                        };
+                        tick(-1);
+                        tick(0);
+                        i8g::gemm_ar(d->SA, d->sa_persistent ? r0 * nao : 0, nr * nao, d->SC, d->d_Y2, (long)nr * nocc, nao, st);
+                        tick(1);
+                        i8g::split_rows(d->SY, d->d_Y2, (long)nr * nocc, nao, nr * nocc, d->k_slices, st);
+                        tick(2);
+                        i8g::gemm(d->SY, d->SY, d->d_vk + (size_t)s * n2, nao, 0, true, st);
+                        tick(3);
+                        if (prof && r0 + kb >= naux) {
+                            fprintf(stderr, "[df-k profile] zeroY2 %.2f ms, gemm1 %.2f ms, splitY %.2f ms, gemm2 %.2f ms (sum over blocks, kb=%d)\n",
+                                    tacc[0], tacc[1], tacc[2], tacc[3], kb);
+                            for (double& t : tacc) t = 0;
+                        }
+                        launches += 3;
+                        continue;
+                    }
                     if (use_occ) {
                         // Y_P (col-major [nao, nocc]) = A_P * Ctilde ; buffers: occ row-major [nao,nocc] == col-major [nocc,nao]
                         CKB(cublasDgemmStridedBatched(d->cublas, CUBLAS_OP_N, CUBLAS_OP_T, nao, nocc, nao, &one, d->d_A, nao, n2,
@@ -645,6 +734,9 @@ extern "C" int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao
 #endif
                 }
             }
+#ifndef B200JK_EMULATE
+            if (use_occ && d->k_mode == 1) { MirrorUpperFn mf{d->d_vk, nao}; for (int s = 0; s < n_dm; s++) { mf.a = d->d_vk + (size_t)s * n2; launch_1d(n2, mf, st); launches++; } }
+#endif
             d2h(vk, d->d_vk, (size_t)n_dm * n2 * 8, st);
         }
 #ifndef B200JK_EMULATE
@@ -658,5 +750,13 @@ extern "C" int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao
         h->stats.ms_total = std::chrono::duration<double, std::milli>(t1 - t0).count();
         h->stats.kernel_launches = launches;
     } catch (std::exception& e) { set_err(h, e.what()); return 2; }
+    return 0;
+}
+
+extern "C" int b200jk_df_set_kmode(b200jk_handle h, int mode, int nslices)
+{
+    if (!h || !h->df) { set_err(h, "call b200jk_df_build first"); return 1; }
+    if (mode < 0 || mode > 1 || nslices < 1 || nslices > 8) { set_err(h, "bad k mode / slice count"); return 1; }
+    h->df->k_mode = mode; h->df->k_slices = nslices;
     return 0;
 }

@@ -41,17 +41,59 @@ void SliceStack::alloc(int rows, int k, int ns_)
     size_t need = (size_t)ns * Rp * Kp;
     if (need > cap) { dev_free(q); q = (int8_t*)dev_alloc(need); cap = need; }
     if (Rp > ecap) { dev_free(E); E = (int*)dev_alloc((size_t)Rp * 4); ecap = Rp; }
+    if (!maxbits_cap || (size_t)Rp > maxbits_cap) { dev_free(maxbits); maxbits = (unsigned long long*)dev_alloc((size_t)Rp * 8); maxbits_cap = Rp; }
 }
-void SliceStack::release() { dev_free(q); dev_free(E); q = nullptr; E = nullptr; cap = 0; ecap = 0; }
+void SliceStack::release() { dev_free(q); dev_free(E); dev_free(maxbits); q = nullptr; E = nullptr; maxbits = nullptr; cap = 0; ecap = 0; maxbits_cap = 0; }
+
+// rows [row0, row0+rows) of an already allocated stack (S.alloc(total_rows, k, ns) + zero fill done by the caller)
+void split_rows_into(SliceStack& S, int row0, const double* X, long ldx, int rows, cudaStream_t st)
+{
+    split_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(X, ldx, rows, S.K, S.Rp, S.Kp, S.ns, row0, S.q, S.E);
+    CK(cudaGetLastError());
+}
 
 void split_rows(SliceStack& S, const double* X, long ldx, int rows, int k, int ns, cudaStream_t st)
 {
     S.alloc(rows, k, ns);
-    split_rows_kernel<<<(S.Rp + 7) / 8, 256, 0, st>>>(X, ldx, rows, k, S.Rp, S.Kp, ns, S.q, S.E);
+    if (S.Rp > rows) {   // zero the pad rows of every slice
+        for (int s = 0; s < ns; s++)
+            CK(cudaMemsetAsync(S.q + ((size_t)s * S.Rp + rows) * S.Kp, 0, (size_t)(S.Rp - rows) * S.Kp, st));
+        CK(cudaMemsetAsync(S.E + rows, 0, (size_t)(S.Rp - rows) * 4, st));
+    }
+    if ((long)k >= 8192 && rows < 4096) {
+        const long seglen = 8192;
+        unsigned nseg = (unsigned)((S.Kp + seglen - 1) / seglen);
+        CK(cudaMemsetAsync(S.maxbits, 0, (size_t)rows * 8, st));
+        rowmax_kernel<<<dim3(nseg, rows), 256, 0, st>>>(X, ldx, k, seglen, S.maxbits);
+        split_long_kernel<<<dim3(nseg, rows), 256, 0, st>>>(X, ldx, k, S.Rp, S.Kp, ns, seglen, S.maxbits, S.q, S.E);
+    } else {
+        split_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(X, ldx, rows, k, S.Rp, S.Kp, ns, 0, S.q, S.E);
+    }
     CK(cudaGetLastError());
 }
 
-void gemm(const SliceStack& A, const SliceStack& B, double* C, long ldc, int inner, bool symmetric, cudaStream_t st)
+// stage-1 GEMM of DF-K with all slice-pair groups resident in TMEM (i8gemm_ar_kernel): rows [a_row0, a_row0+M) of A
+void gemm_ar(const SliceStack& A, int a_row0, int M, const SliceStack& B, double* C, long ldc, int inner, cudaStream_t st)
+{
+    if (A.Kp != B.Kp || A.ns != B.ns) throw std::runtime_error("i8gemm_ar: operand stacks disagree");
+    if (A.ns * AR_BN > 512) throw std::runtime_error("i8gemm_ar: too many slices for TMEM");
+    static bool configured = false;
+    if (!configured) {
+        CK(cudaFuncSetAttribute(i8gemm_ar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM_BYTES));
+        configured = true;
+    }
+    CUtensorMap ta, tb;
+    make_tmap(&ta, A.q, (uint64_t)A.ns * A.Rp, A.Kp, BM);
+    make_tmap(&tb, B.q, (uint64_t)B.ns * B.Rp, B.Kp, AR_BN);
+    GemmParams P{};
+    P.M = M; P.N = B.R; P.Kp = A.Kp; P.Mp = A.Rp; P.Np = B.Rp; P.ns = A.ns; P.symmetric = 0;
+    P.Ea = A.E; P.Eb = B.E; P.C = C; P.ldc = ldc; P.inner = inner; P.a_row0 = a_row0; P.ksplit = 1; P.dbg = nullptr;
+    dim3 grid((B.R + AR_BN - 1) / AR_BN, (M + BM - 1) / BM);
+    i8gemm_ar_kernel<<<grid, NTHREADS, AR_SMEM_BYTES, st>>>(ta, tb, P);
+    CK(cudaGetLastError());
+}
+
+void gemm(const SliceStack& A, const SliceStack& B, double* C, long ldc, int inner, bool symmetric, cudaStream_t st, long long* dbg)
 {
     if (A.Kp != B.Kp || A.ns != B.ns) throw std::runtime_error("i8gemm: operand stacks disagree");
     static bool configured = false;
@@ -64,8 +106,23 @@ void gemm(const SliceStack& A, const SliceStack& B, double* C, long ldc, int inn
     make_tmap(&tb, B.q, (uint64_t)B.ns * B.Rp, B.Kp, BN);
     GemmParams P{};
     P.M = A.R; P.N = B.R; P.Kp = A.Kp; P.Mp = A.Rp; P.Np = B.Rp; P.ns = A.ns; P.symmetric = symmetric ? 1 : 0;
-    P.Ea = A.E; P.Eb = B.E; P.C = C; P.ldc = ldc; P.inner = inner;
-    dim3 grid((B.R + BN - 1) / BN, (A.R + BM - 1) / BM);
+    P.Ea = A.E; P.Eb = B.E; P.C = C; P.ldc = ldc; P.inner = inner; P.dbg = dbg; P.a_row0 = 0;
+    const int mtiles = (A.R + BM - 1) / BM, ntiles = (B.R + BN - 1) / BN;
+    int tiles = 0;
+    for (int mt = 0; mt < mtiles; mt++)
+        for (int nt = 0; nt < ntiles; nt++)
+            if (!(symmetric && (nt + 1) * BN <= mt * BM)) tiles++;
+    int nkb = A.Kp / BK;
+    // split K so that the CTAs fill one (or two) waves of 148 SMs as exactly as possible, >= 8 K blocks each
+    int ksplit = 1, best_waste = 1 << 30;
+    for (int ks = 1; ks <= 64 && ks * 8 <= std::max(nkb, 8); ks++) {
+        int ctas = tiles * ks, waves = (ctas + 147) / 148;
+        if (waves > 2) break;
+        int waste = (waves * 148 - ctas) * 1000 / (waves * 148);
+        if (waste < best_waste || (waste == best_waste && ks > ksplit)) { best_waste = waste; ksplit = ks; }
+    }
+    P.ksplit = ksplit;
+    dim3 grid((B.R + BN - 1) / BN, (A.R + BM - 1) / BM, ksplit);
     i8gemm_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tb, P);
     CK(cudaGetLastError());
 }
@@ -95,10 +152,20 @@ extern "C" int b200jk_i8gemm_test(b200jk_handle h, int M, int N, int K, const do
         split_rows(SA, dA, K, M, K, ns, st);
         split_rows(SB, dB, K, N, K, ns, st);
         CK(cudaEventRecord(h->ev0, st));
-        gemm(SA, SB, dC, N, 0, symmetric != 0, st);
+        long long* ddbg = (long long*)dev_alloc(64 * 8);
+        dev_zero(ddbg, 64 * 8, st);
+        gemm(SA, SB, dC, N, 0, symmetric != 0, st, ddbg);
         CK(cudaEventRecord(h->ev1, st));
         d2h(C, dC, (size_t)M * N * 8, st);
+        long long hd[64];
+        d2h(hd, ddbg, 64 * 8, st);
         CK(cudaStreamSynchronize(st));
+        if (getenv("B200JK_I8_DEBUG")) {
+            fprintf(stderr, "i8gemm cycles (CTA 0,0) rel. to start:");
+            for (int i = 8; i < 8 + 4 * ns; i++) fprintf(stderr, "%s%lld", (i % 4 == 0) ? " | " : " ", hd[i] ? hd[i] - hd[0] : -1);
+            fprintf(stderr, "\n");
+        }
+        dev_free(ddbg);
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         h->stats.ms_kernels = ms;

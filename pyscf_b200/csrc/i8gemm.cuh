@@ -28,7 +28,8 @@ constexpr int NSTAGE = 4;
 constexpr int MAXS = 8;        // max slices
 constexpr int A_STAGE_BYTES = BM * BK;
 constexpr int B_STAGE_BYTES = BN * BK;
-constexpr int SMEM_BYTES = NSTAGE * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_STAGE_INTS = 32 * 33;   // per epilogue warp: 32x32 int32 transpose buffer, padded
+constexpr int SMEM_BYTES = NSTAGE * (A_STAGE_BYTES + B_STAGE_BYTES) + 4 * EPI_STAGE_INTS * 4 + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int NTHREADS = 192;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2..5 epilogue
 
 struct GemmParams {
@@ -41,6 +42,9 @@ struct GemmParams {
     // optional transposed-scatter epilogue (stage 1 of DF-K): C element (m, n) is stored at
     //   C[(m % inner) * ldc + (m / inner) * N + n]   when inner > 0
     int inner;
+    int a_row0;            // first row of the A stack used by this GEMM (row blocks of a persistent stack)
+    int ksplit;            // K blocks are divided among gridDim.z CTAs (fp64 reductions make this safe)
+    long long* dbg;        // optional cycle stamps of CTA (0,0) (tests/tuning)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -165,11 +169,17 @@ i8gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
     uint64_t* tfull = bars + 2 * NSTAGE;   // [2]
     uint64_t* tempty = bars + 2 * NSTAGE + 2;  // [2]
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * NSTAGE + 4);
+    int* epi_stage = (int*)(smem + NSTAGE * (A_STAGE_BYTES + B_STAGE_BYTES) + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt = blockIdx.y, nt = blockIdx.x;
     if (P.symmetric && (nt + 1) * BN <= mt * BM) return;   // tile entirely below the diagonal
-    const int nkb = P.Kp / BK;
+    const int nkb_all = P.Kp / BK;
+    const int kb_per = (nkb_all + P.ksplit - 1) / P.ksplit;
+    const int kb0 = blockIdx.z * kb_per;
+    const int kb1 = (kb0 + kb_per < nkb_all) ? kb0 + kb_per : nkb_all;
+    const int nkb = kb1 - kb0;
+    if (nkb <= 0) return;
     const int ns = P.ns;
 
     if (warp == 0 && lane == 0) {
@@ -184,6 +194,8 @@ i8gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const bool dbg_on = P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    if (dbg_on && threadIdx.x == 0) P.dbg[0] = clock64();
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -195,8 +207,8 @@ i8gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                     for (int kb = 0; kb < nkb; kb++) {
                         mbar_wait(&empty[stage], phase ^ 1);
                         mbar_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-                        tma_load_2d(sA + stage * A_STAGE_BYTES, &tmapA, &full[stage], kb * BK, k * P.Mp + mt * BM);
-                        tma_load_2d(sB + stage * B_STAGE_BYTES, &tmapB, &full[stage], kb * BK, l * P.Np + nt * BN);
+                        tma_load_2d(sA + stage * A_STAGE_BYTES, &tmapA, &full[stage], (kb0 + kb) * BK, k * P.Mp + P.a_row0 + mt * BM);
+                        tma_load_2d(sB + stage * B_STAGE_BYTES, &tmapB, &full[stage], (kb0 + kb) * BK, l * P.Np + nt * BN);
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -211,6 +223,7 @@ i8gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                 const int buf = it & 1;
                 const uint32_t tphase = (it >> 1) & 1;
                 mbar_wait(&tempty[buf], tphase ^ 1);          // epilogue has drained this accumulator
+                if (dbg_on) P.dbg[8 + 4 * it] = clock64();
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + buf * BN;
                 uint32_t acc = 0;
@@ -228,43 +241,50 @@ i8gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                     }
                 mma_commit(&tfull[buf]);                      // accumulator of group g complete
+                if (dbg_on) P.dbg[9 + 4 * it] = clock64();
             }
         }
     } else {
-        // ===== epilogue warps: TMEM -> registers -> fp64 scale -> C =====
+        // ===== epilogue warps: TMEM -> registers -> smem transpose -> coalesced fp64 read-modify-write of C =====
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;
-        const int m = mt * BM + row;
-        const bool mrow_ok = m < P.M;
-        const double sa = mrow_ok ? pow2i(P.Ea[m]) : 0.0;
+        int* stg = epi_stage + q * EPI_STAGE_INTS;
+        const int mrow0 = mt * BM + q * 32;      // first row of this warp's 32-row band
         int it = 0;
         for (int g = ns - 1; g >= 0; g--, it++) {
             const int buf = it & 1;
             const uint32_t tphase = (it >> 1) & 1;
             mbar_wait(&tfull[buf], tphase);
             tc_fence_after();
-            const double sg = sa * pow2i(-12 - 7 * g);
+            if (dbg_on && q == 0 && lane == 0) P.dbg[10 + 4 * it] = clock64();
+            const int eg = -12 - 7 * g;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c0, r);
-                const int n0 = nt * BN + c0;
-                if (mrow_ok && n0 < P.N) {
-                    double* crow;
-                    if (P.inner > 0) crow = P.C + (long)(m % P.inner) * P.ldc + (long)(m / P.inner) * P.N;
-                    else crow = P.C + (long)m * P.ldc;
+                const int n = nt * BN + c0 + lane;       // this lane's column after the transpose
+                if (nt * BN + c0 >= P.N) continue;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const int n = n0 + j;
-                        if (n < P.N && (!P.symmetric || n >= m)) {
-                            const double v = (double)(int)r[j] * sg * pow2i(P.Eb[n]);
-                            crow[n] += v;
-                        }
+                for (int j = 0; j < 32; j++) stg[lane * 33 + j] = (int)r[j];
+                __syncwarp();
+                const bool ncol_ok = n < P.N;
+                const int ebn = ncol_ok ? P.Eb[n] : 0;
+#pragma unroll 4
+                for (int rr = 0; rr < 32; rr++) {
+                    const int m = mrow0 + rr;
+                    if (m >= P.M) break;
+                    if (ncol_ok && (!P.symmetric || n >= m)) {
+                        const double v = (double)stg[rr * 33 + lane] * pow2i(P.Ea[P.a_row0 + m] + ebn + eg);
+                        double* dst;
+                        if (P.inner > 0) dst = P.C + (long)(m % P.inner) * P.ldc + (long)(m / P.inner) * P.N + n;
+                        else dst = P.C + (long)m * P.ldc + n;
+                        atomicAdd(dst, v);   // RED.ADD.F64: no read latency, safe under split-K
                     }
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
+            if (dbg_on && q == 0 && lane == 0) P.dbg[11 + 4 * it] = clock64();
             if (lane == 0) mbar_arrive(&tempty[buf]);
         }
     }
@@ -273,30 +293,208 @@ i8gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// ---------------------------------------------------------------------------------------------- slicing kernel
-// X: [R, K] fp64 row-major (row stride ldx).  out: [ns][Rp][Kp] int8 (rows >= R and cols >= K zero).  E[r] exponents.
-// One warp per row.
+// ---------------------------------------------------------------------------------------------- GEMM kernel, "all groups resident"
+// Variant for a SHORT contraction (K = nao) and a narrow N (stage 1 of DF-K: N = nocc): tile 128 x 64 with ALL slice-pair
+// groups resident in TMEM (group g at columns g*64, ns*64 <= 512).  The A_k tile is loaded ONCE per (K block, k) and
+// reused for every B_l (A-stationary: no operand re-reads), and there is ONE epilogue that combines the groups in
+// fp64 registers and stores each output once (no read-modify-write, no zero fill).
+constexpr int AR_BN = 64;
+constexpr int AR_NSA = 4, AR_NSB = 2;            // A ring: one slice tile per stage; B ring: ALL slices of a K block per stage
+constexpr int AR_A_BYTES = BM * BK, AR_B1_BYTES = AR_BN * BK, AR_B_BYTES = MAXS * AR_B1_BYTES;
+constexpr int AR_SMEM_BYTES = AR_NSA * AR_A_BYTES + AR_NSB * AR_B_BYTES + 4 * EPI_STAGE_INTS * 4 + 1024 + 512;
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const GemmParams P)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + AR_NSA * AR_A_BYTES;
+    uint64_t* bars = (uint64_t*)(smem + AR_NSA * AR_A_BYTES + AR_NSB * AR_B_BYTES);
+    uint64_t* afull = bars;                      // [AR_NSA]
+    uint64_t* aempty = afull + AR_NSA;
+    uint64_t* bfull = aempty + AR_NSA;           // [AR_NSB]
+    uint64_t* bempty = bfull + AR_NSB;
+    uint64_t* tfull = bempty + AR_NSB;           // [1]
+    uint32_t* tmem_slot = (uint32_t*)(tfull + 1);
+    int* epi_stage = (int*)(smem + AR_NSA * AR_A_BYTES + AR_NSB * AR_B_BYTES + 512);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = blockIdx.y, nt = blockIdx.x;
+    const int nkb = P.Kp / BK;
+    const int ns = P.ns;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmapA);
+        prefetch_tmap(&tmapB);
+        for (int i = 0; i < AR_NSA; i++) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+        for (int i = 0; i < AR_NSB; i++) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            for (int kb = 0; kb < nkb; kb++) {
+                mbar_wait(&bempty[sb], pb ^ 1);
+                mbar_expect_tx(&bfull[sb], ns * AR_B1_BYTES);
+                for (int l = 0; l < ns; l++)
+                    tma_load_2d(sB + sb * AR_B_BYTES + l * AR_B1_BYTES, &tmapB, &bfull[sb], kb * BK, l * P.Np + nt * AR_BN);
+                if (++sb == AR_NSB) { sb = 0; pb ^= 1; }
+                for (int k = 0; k < ns; k++) {
+                    mbar_wait(&aempty[sa], pa ^ 1);
+                    mbar_expect_tx(&afull[sa], AR_A_BYTES);
+                    tma_load_2d(sA + sa * AR_A_BYTES, &tmapA, &afull[sa], kb * BK, k * P.Mp + P.a_row0 + mt * BM);
+                    if (++sa == AR_NSA) { sa = 0; pa ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_i8(BM, AR_BN);
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            for (int kb = 0; kb < nkb; kb++) {
+                mbar_wait(&bfull[sb], pb);
+                tc_fence_after();
+                const uint32_t bbase = smem_u32(sB + sb * AR_B_BYTES);
+                for (int k = 0; k < ns; k++) {
+                    mbar_wait(&afull[sa], pa);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(sA + sa * AR_A_BYTES);
+                    for (int l = 0; l < ns - k; l++) {
+                        const uint32_t b0 = bbase + l * AR_B1_BYTES;
+                        const uint32_t tacc = tmem_base + (k + l) * AR_BN;
+                        uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;   // first touch of group k+l is (kb=0, k=0)
+#pragma unroll
+                        for (int kk = 0; kk < BK / UK; kk++) {
+                            mma_i8(tacc, make_desc_k_sw128(a0 + kk * UK), make_desc_k_sw128(b0 + kk * UK), idesc, acc);
+                            acc = 1;
+                        }
+                    }
+                    mma_commit(&aempty[sa]);
+                    if (++sa == AR_NSA) { sa = 0; pa ^= 1; }
+                }
+                mma_commit(&bempty[sb]);
+                if (++sb == AR_NSB) { sb = 0; pb ^= 1; }
+            }
+            mma_commit(tfull);
+        }
+    } else {
+        const int q = warp & 3;
+        int* stg = epi_stage + q * EPI_STAGE_INTS;
+        const int mrow0 = mt * BM + q * 32;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < AR_BN; c0 += 32) {
+            const int n = nt * AR_BN + c0 + lane;
+            if (nt * AR_BN + c0 >= P.N) break;
+            // combine the groups in fp64 (smallest weight first), row = this lane
+            double accv[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) accv[j] = 0.0;
+            for (int g = ns - 1; g >= 0; g--) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + g * AR_BN + c0, r);
+                const double w = pow2i(-12 - 7 * g);
+#pragma unroll
+                for (int j = 0; j < 32; j++) accv[j] += (double)(int)r[j] * w;
+            }
+            // transpose through shared memory in two 32-bit halves so that a warp stores one output row segment
+            const bool ncol_ok = n < P.N;
+            const int ebn = ncol_ok ? P.Eb[n] : 0;
+            unsigned int lo[32], hi[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) stg[lane * 33 + j] = (int)(__double_as_longlong(accv[j]) & 0xffffffffLL);
+            __syncwarp();
+#pragma unroll
+            for (int rr = 0; rr < 32; rr++) lo[rr] = (unsigned int)stg[rr * 33 + lane];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; j++) stg[lane * 33 + j] = (int)(__double_as_longlong(accv[j]) >> 32);
+            __syncwarp();
+#pragma unroll
+            for (int rr = 0; rr < 32; rr++) hi[rr] = (unsigned int)stg[rr * 33 + lane];
+            __syncwarp();
+            double outv[32];
+#pragma unroll
+            for (int rr = 0; rr < 32; rr++) outv[rr] = __longlong_as_double(((long long)hi[rr] << 32) | (long long)lo[rr]);
+#pragma unroll
+            for (int rr = 0; rr < 32; rr++) {
+                const int m = mrow0 + rr;
+                if (ncol_ok && m < P.M) {
+                    const double v = outv[rr] * pow2i(P.Ea[P.a_row0 + m] + ebn);
+                    double* dst;
+                    if (P.inner > 0) dst = P.C + (long)(m % P.inner) * P.ldc + (long)(m / P.inner) * P.N + n;
+                    else dst = P.C + (long)m * P.ldc + n;
+                    *dst = v;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------- slicing kernels
+// X: [R, K] fp64 row-major (row stride ldx).  out: [ns][Rp][Kp] int8, rows written at out_row0 + r; E[out_row0 + r].
+// Pad rows / pad columns of the stack must be zero (stack_alloc memsets once; pad columns are rewritten here).
+// (1) one warp per row: many short rows (the unpacked tensor: K = nao).
 __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restrict__ X, long ldx, int R, int K, int Rp, int Kp, int ns,
-                                                         int8_t* __restrict__ out, int* __restrict__ E)
+                                                         int out_row0, int8_t* __restrict__ out, int* __restrict__ E)
 {
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (r >= Rp) return;
-    if (r >= R) {
-        for (int s = 0; s < ns; s++)
-            for (int k = lane; k < Kp; k += 32) out[((long)s * Rp + r) * Kp + k] = 0;
-        if (lane == 0) E[r] = 0;
-        return;
-    }
+    if (r >= R) return;
     const double* x = X + (long)r * ldx;
     double mx = 0.0;
     for (int k = lane; k < K; k += 32) mx = fmax(mx, fabs(x[k]));
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     int e = 0;
     if (mx > 0.0) { frexp(mx, &e); }         // mx = f * 2^e, f in [0.5,1)  =>  |x| / 2^e < 1
-    if (lane == 0) E[r] = e;
+    if (lane == 0) E[out_row0 + r] = e;
     const double sc = ldexp(1.0, 6 - e);
     for (int k = lane; k < Kp; k += 32) {
+        double rr = (k < K) ? x[k] * sc : 0.0;
+        for (int s = 0; s < ns; s++) {
+            double qv = rint(rr);
+            out[((long)s * Rp + out_row0 + r) * Kp + k] = (int8_t)(int)qv;
+            rr = (rr - qv) * 128.0;
+        }
+    }
+}
+// (2) few long rows (Y: K = naux_block * nocc): grid (segments, rows); row maxima through 64-bit atomicMax on |x| bits
+__global__ void __launch_bounds__(256) rowmax_kernel(const double* __restrict__ X, long ldx, int K, long seglen,
+                                                     unsigned long long* __restrict__ maxbits)
+{
+    const int r = blockIdx.y;
+    const long k0 = blockIdx.x * seglen, k1 = (k0 + seglen < K) ? k0 + seglen : K;
+    const double* x = X + (long)r * ldx;
+    double mx = 0.0;
+    for (long k = k0 + threadIdx.x; k < k1; k += 256) mx = fmax(mx, fabs(x[k]));
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(&maxbits[r], (unsigned long long)__double_as_longlong(mx));
+}
+__global__ void __launch_bounds__(256) split_long_kernel(const double* __restrict__ X, long ldx, int K, int Rp, int Kp, int ns, long seglen,
+                                                         const unsigned long long* __restrict__ maxbits, int8_t* __restrict__ out,
+                                                         int* __restrict__ E)
+{
+    const int r = blockIdx.y;
+    const long k0 = blockIdx.x * seglen, k1 = (k0 + seglen < Kp) ? k0 + seglen : Kp;
+    const double* x = X + (long)r * ldx;
+    const double mx = __longlong_as_double((long long)maxbits[r]);
+    int e = 0;
+    if (mx > 0.0) { frexp(mx, &e); }
+    if (blockIdx.x == 0 && threadIdx.x == 0) E[r] = e;
+    const double sc = ldexp(1.0, 6 - e);
+    for (long k = k0 + threadIdx.x; k < k1; k += 256) {
         double rr = (k < K) ? x[k] * sc : 0.0;
         for (int s = 0; s < ns; s++) {
             double qv = rint(rr);
@@ -308,3 +506,4 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restric
 
 }  // namespace i8g
 }  // namespace b200jk
+

@@ -8,11 +8,15 @@ struct SliceStack {      // [ns][Rp][Kp] int8 slices + per-row exponents, device
     int8_t* q = nullptr; int* E = nullptr;
     int R = 0, K = 0, Rp = 0, Kp = 0, ns = 0;
     size_t cap = 0; int ecap = 0;
+    unsigned long long* maxbits = nullptr; size_t maxbits_cap = 0;
     void alloc(int rows, int k, int ns);
     void release();
 };
 void split_rows(SliceStack& S, const double* X, long ldx, int rows, int k, int ns, cudaStream_t st);
+void split_rows_into(SliceStack& S, int row0, const double* X, long ldx, int rows, cudaStream_t st);
+void gemm_ar(const SliceStack& A, int a_row0, int M, const SliceStack& B, double* C, long ldc, int inner, cudaStream_t st);
 // C[m*ldc + n] (or the transposed scatter when inner>0, see GemmParams) += A B^T
-void gemm(const SliceStack& A, const SliceStack& B, double* C, long ldc, int inner, bool symmetric, cudaStream_t st);
+void gemm(const SliceStack& A, const SliceStack& B, double* C, long ldc, int inner, bool symmetric, cudaStream_t st,
+          long long* dbg = nullptr);
 }  // namespace i8g
 }  // namespace b200jk

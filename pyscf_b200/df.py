@@ -29,6 +29,8 @@ class DF:
         self.omega = None
         self.lindep = 1e-7         # pyscf/df/incore.py:30-33 LINEAR_DEP_THR
         self.blockdim = 240        # pyscf/df/df.py:95 (loop() default block size)
+        self.k_engine = 'tcgen05'
+        self.k_slices = 7
         self.verbose = getattr(mol, 'verbose', 0)
         self.stdout = getattr(mol, 'stdout', None)
         self.max_memory = getattr(mol, 'max_memory', 4000)
@@ -49,6 +51,15 @@ class DF:
                                       omega, self.lindep), 'b200jk_df_build')
         self._handle = h
         self.nao = int(mol.ao_loc_nr(cart=False)[-1])
+        self.set_k_engine(self.k_engine, self.k_slices)
+        return self
+
+    def set_k_engine(self, engine='tcgen05', nslices=7):
+        """'tcgen05' (int8-slice tensor-core GEMMs, default) or 'dgemm' (cuBLAS FP64 yardstick)."""
+        self.k_engine, self.k_slices = engine, nslices
+        if self._handle is not None:
+            h = self._handle
+            h.check(h.lib.b200jk_df_set_kmode(h._h, 1 if engine == 'tcgen05' else 0, nslices), 'b200jk_df_set_kmode')
         return self
 
     def reset(self, mol=None):

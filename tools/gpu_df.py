@@ -13,8 +13,14 @@ rng = np.random.RandomState(1)
 c,_ = np.linalg.qr(rng.standard_normal((nao,nocc)))
 occ = np.full(nocc, 2.0)
 dm = TaggedDM((c*occ).dot(c.T), mo_coeff=c, mo_occ=occ)
-for it in range(3):
-    t=time.time(); vj,vk = d.get_jk(dm); print('get_jk (occ path) s', time.time()-t, d.stats()['ms_kernels'], flush=True)
-t=time.time(); vj2,vk2 = d.get_jk(np.asarray(dm)); print('get_jk (general dm) s', time.time()-t)
-print('occ vs general', abs(vj-vj2).max(), abs(vk-vk2).max())
+res = {}
+for eng in ['dgemm','tcgen05']:
+    d.set_k_engine(eng, 7)
+    for it in range(3):
+        t=time.time(); vj,vk = d.get_jk(dm); dt=time.time()-t
+    print(eng, 'get_jk s', dt, 'kernels ms', d.stats()['ms_kernels'], flush=True)
+    res[eng]=vk
+print('tcgen05 vs dgemm  max|dK|', abs(res['tcgen05']-res['dgemm']).max(), ' max|K|', abs(res['dgemm']).max())
+for ns in [5,6,8]:
+    d.set_k_engine('tcgen05', ns); _,vk = d.get_jk(dm); print('ns',ns,'err', abs(vk-res['dgemm']).max(), d.stats()['ms_kernels'])
 t=time.time(); vj3,_ = d.get_jk(dm, with_k=False); print('J only s', time.time()-t, d.stats()['ms_kernels'])
