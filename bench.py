@@ -35,6 +35,8 @@ WORKLOADS = {
     'benzene-ccpvtz-direct': dict(geom='benzene', basis='cc-pvtz', nocc=21, kind='direct'),
     'benzene-ccpvdz-direct': dict(geom='benzene', basis='cc-pvdz', nocc=21, kind='direct'),
     'h2o-ccpvdz-direct': dict(geom='h2o', basis='cc-pvdz', nocc=5, kind='direct'),
+    'c60-def2svp-df': dict(geom='c60', basis='def2-svp', nocc=180, kind='df'),
+    'benzene-def2svp-df': dict(geom='benzene', basis='def2-svp', nocc=21, kind='df'),
 }
 
 def scf_like_dm(nao, nocc, seed=1):
@@ -107,36 +109,53 @@ def run_ours(args, rank, world):
     import torch
     import ctypes
     from pyscf_b200.jk import VHFOpt
-    from pyscf_b200 import lib as _lib
+    from pyscf_b200.df import DF, TaggedDM
     w = WORKLOADS[args.workload]
+    is_df = w['kind'] == 'df'
     local = int(os.environ.get('LOCAL_RANK', rank))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
     mol = build_mol(w)
     nao = mol.nao
-    dm_h = scf_like_dm(nao, w['nocc'])
+    rng = np.random.RandomState(1)
+    c_occ, _ = np.linalg.qr(rng.standard_normal((nao, w['nocc'])))
+    dm_h = 2.0 * c_occ.dot(c_occ.T)
+    occ_h = np.ascontiguousarray(c_occ * np.sqrt(2.0))
     t0 = time.time()
-    opt = VHFOpt(mol, direct_scf_tol=1e-13, device=local)
+    if is_df:
+        eng = DF(mol, device=local).build()
+        h = eng._handle
+    else:
+        eng = VHFOpt(mol, direct_scf_tol=1e-13, device=local)
+        h = eng.handle
     setup_s = time.time() - t0
-    h = opt.handle
+    # strong scaling: ONE Fock build is split over the ranks (shell-pair batches / auxiliary rows), partial J,K
+    # are summed by a single NCCL all-reduce per build
+    h.check(h.lib.b200jk_set_shard(h._h, rank, world), 'b200jk_set_shard')
     stream = torch.cuda.current_stream(dev)
     h.lib.b200jk_set_stream(h._h, ctypes.c_void_p(stream.cuda_stream))
 
     dm_d = torch.from_numpy(dm_h).to(dev)
-    vj_d = torch.empty_like(dm_d)
-    vk_d = torch.empty_like(dm_d)
+    occ_d = torch.from_numpy(occ_h).to(dev)
+    out_d = torch.zeros((2, nao, nao), dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
 
     def step_device():
-        rc = h.lib.b200jk_direct_jk_device(h._h, ctypes.c_void_p(dm_d.data_ptr()), 1, nao, 1,
-                                           ctypes.c_void_p(vj_d.data_ptr()), ctypes.c_void_p(vk_d.data_ptr()))
-        h.check(rc, 'b200jk_direct_jk_device')
+        if is_df:
+            rc = h.lib.b200jk_df_jk_device(h._h, ctypes.c_void_p(dm_d.data_ptr()), 1, nao, ctypes.c_void_p(occ_d.data_ptr()),
+                                           w['nocc'], 1, ctypes.c_void_p(out_d[0].data_ptr()), ctypes.c_void_p(out_d[1].data_ptr()))
+            h.check(rc, 'b200jk_df_jk_device')
+        else:
+            rc = h.lib.b200jk_direct_jk_device(h._h, ctypes.c_void_p(dm_d.data_ptr()), 1, nao, 1,
+                                               ctypes.c_void_p(out_d[0].data_ptr()), ctypes.c_void_p(out_d[1].data_ptr()))
+            h.check(rc, 'b200jk_direct_jk_device')
+        if world > 1:
+            dist.all_reduce(out_d)
 
-    # weak scaling: every rank builds J/K for its own density (independent SCF replicas share nothing);
-    # strong scaling of ONE build (quartet sharding + all-reduce) is reported by --scaling strong when built.
     for _ in range(args.warmup):
         step_device()
     torch.cuda.synchronize()
@@ -152,6 +171,8 @@ def run_ours(args, rank, world):
     t_wall0 = time.time()
     for k in range(args.steps):
         flush.zero_()
+        if world > 1:
+            dist.barrier()
         evs[k][0].record(stream)
         step_device()
         evs[k][1].record(stream)
@@ -163,17 +184,34 @@ def run_ours(args, rank, world):
     t_wall = time.time() - t_wall0
     step_ms = [a.elapsed_time(b) for a, b in evs]
     ms_per_step = float(np.mean(step_ms))
-    # ---- end-to-end through the public plugin call with pinned host buffers
-    dm_pin = torch.from_numpy(dm_h).pin_memory()
-    dm_pin_np = dm_pin.numpy()
+    vj_dev = out_d[0].cpu().numpy().copy()
+    vk_dev = out_d[1].cpu().numpy().copy()
+    # ---- end-to-end through the public plugin call with pinned host buffers (H2D + D2H inside the timed region)
+    dm_pin = torch.from_numpy(dm_h).pin_memory().numpy()
+    if is_df:
+        dm_pub = TaggedDM(dm_pin, mo_coeff=c_occ, mo_occ=np.full(w['nocc'], 2.0))
+    else:
+        dm_pub = dm_pin
+    h.lib.b200jk_set_stream(h._h, None)
+
+    def step_public():
+        if world > 1:
+            from pyscf_b200.parallel import ShardedJK
+            if not hasattr(step_public, 'sj'):
+                step_public.sj = ShardedJK(eng, rank, world)
+            return step_public.sj.get_jk(dm_pub, hermi=1)
+        return eng.get_jk(dm_pub, hermi=1)
+
     for _ in range(2):
-        opt.get_jk(dm_pin_np, hermi=1)
+        step_public()
     e2e_ms = []
     for k in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t = time.perf_counter()
-        vj, vk = opt.get_jk(dm_pin_np, hermi=1)
+        vj, vk = step_public()
         e2e_ms.append((time.perf_counter() - t) * 1e3)
     clocks = sampler.finish()
     e2e_ms_mean = float(np.mean(e2e_ms))
@@ -184,11 +222,10 @@ def run_ours(args, rank, world):
         ms_per_step, e2e_ms_mean = float(tt[0]), float(tt[1])
 
     if rank != 0:
+        if world > 1:
+            dist.barrier()
         return
-    # ---- roofline of the class kernels
-    peak = ctypes.c_double(0)
-    h.lib.b200jk_set_stream(h._h, None)
-    h.lib.b200jk_fp64_peak(h._h, ctypes.byref(peak))
+    # ---- roofline
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -196,45 +233,106 @@ def run_ours(args, rank, world):
         pass
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
     kernel_ms = float(np.mean(kern_ms))
-    from pyscf_b200.flops import direct_jk_flops
-    flops, n_eri = direct_jk_flops(mol)
-    bytes_alg = algorithmic_counts(mol, opt)
-    fp64_ach = flops / (kernel_ms * 1e-3) / 1e12 if flops else None
-    roof = {'bound': 'fp64', 'achieved': fp64_ach, 'peak': peak.value, 'unit': 'TFLOP/s',
-            'frac': (fp64_ach / peak.value) if (fp64_ach and peak.value) else None, 'traffic': None,
-            'kernel': 'jk_class_kernel<QClass<LI,LJ,LK,LL,NP>,NQ> (all class launches of one build)',
-            'kernel_ms_per_step': kernel_ms, 'alg_flops_per_step': flops, 'alg_cart_eris_per_step': n_eri,
-            'peak_source': 'b200jk_fp64_peak DFMA micro-benchmark (MEASURED_PEAKS.json has no fp64 entry)',
-            'hbm': {'bound': 'hbm', 'achieved': bytes_alg / (kernel_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
-                    'frac': bytes_alg / (kernel_ms * 1e-3) / 1e9 / hbm_peak, 'alg_bytes_per_step': bytes_alg,
-                    'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650'}}
+    if not is_df:
+        from pyscf_b200.flops import direct_jk_flops
+        peak = ctypes.c_double(0)
+        h.lib.b200jk_fp64_peak(h._h, ctypes.byref(peak))
+        flops, n_eri = direct_jk_flops(mol)
+        bytes_alg = algorithmic_counts(mol, eng)
+        fp64_ach = flops / world / (kernel_ms * 1e-3) / 1e12
+        roof = {'bound': 'fp64', 'achieved': fp64_ach, 'peak': peak.value, 'unit': 'TFLOP/s',
+                'frac': fp64_ach / peak.value if peak.value else None, 'traffic': None,
+                'kernel': 'jk_class_kernel / jk_tpq_kernel <QClass<LI,LJ,LK,LL,NP>> (all class launches of one build)',
+                'kernel_ms_per_step': kernel_ms, 'alg_flops_per_step': flops, 'alg_cart_eris_per_step': n_eri,
+                'peak_source': 'b200jk_fp64_peak DFMA micro-benchmark (MEASURED_PEAKS.json has no fp64 entry)',
+                'hbm': {'bound': 'hbm', 'achieved': bytes_alg / (kernel_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                        'frac': bytes_alg / (kernel_ms * 1e-3) / 1e9 / hbm_peak, 'alg_bytes_per_step': bytes_alg,
+                        'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650'}}
+        path = '4-center direct J/K (hermi=1, with_j, with_k)'
+    else:
+        naux = eng.get_naoaux()
+        ns = eng.k_slices
+        fp64_flops = 4.0 * naux * nao * nao * w['nocc']           # dsymm + dgemm count of the reference
+        int8_ops = fp64_flops * ns * (ns + 1) / 2                  # slice GEMMs actually executed
+        bf16_peak = peaks.get('bf16_tflops_sustained', 1400.0)
+        ach = int8_ops / world / (kernel_ms * 1e-3) / 1e12
+        cderi_bytes = naux * nao * (nao + 1) / 2 * 8
+        roof = {'bound': 'tensor', 'achieved': ach, 'peak': 2 * bf16_peak, 'unit': 'TOP/s (int8)', 'frac': ach / (2 * bf16_peak),
+                'traffic': None, 'kernel': 'i8gemm_ar_kernel + i8gemm_kernel (tcgen05.mma.kind::i8 slice GEMMs of DF-K)',
+                'kernel_ms_per_step': kernel_ms, 'slice_gemms': ns * (ns + 1) // 2, 'fp64_equiv_flops_per_step': fp64_flops,
+                'fp64_equiv_tflops': fp64_flops / world / (kernel_ms * 1e-3) / 1e12,
+                'peak_source': '2 x MEASURED_PEAKS.json bf16_tflops_sustained (int8 dense = 2x bf16 on sm_100a; of measured); '
+                               'kernel_ms covers the whole DF J+K build (J pass, slicing, both GEMM stages)',
+                'hbm': {'bound': 'hbm', 'note': 'DF-J: two streaming passes over cderi', 'alg_bytes_per_step': cderi_bytes,
+                        'peak': hbm_peak, 'unit': 'GB/s'}}
+        path = 'DF J/K (cderi resident, K via tcgen05 int8 slices, %d slices)' % ns
     # ---- CPU baseline (oracle port), rank 0, N=1 only
     cpu = None
     if world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(mol, dm_h, args.workload)
+        if is_df:
+            cpu = cpu_baseline_df(mol, dm_h, c_occ, args.workload)
+        else:
+            cpu = cpu_baseline(mol, dm_h, args.workload)
         if cpu.get('vj') is not None:
-            err_j = float(abs(vj - cpu.pop('vj')).max())
-            err_k = float(abs(vk - cpu.pop('vk')).max())
-            cpu['max_abs_dJ_vs_gpu'] = err_j
-            cpu['max_abs_dK_vs_gpu'] = err_k
+            cpu['max_abs_dJ_vs_gpu'] = float(abs(vj - cpu.pop('vj')).max())
+            cpu['max_abs_dK_vs_gpu'] = float(abs(vk - cpu.pop('vk')).max())
     out = {
-        'metric': 'J/K Fock-build wall-s/iter', 'value': ms_per_step * 1e-3 / 1.0, 'unit': 's',
+        'metric': 'J/K Fock-build wall-s/iter', 'value': ms_per_step * 1e-3, 'unit': 's',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
-        'higher_is_better': False, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'molecule': w['geom'], 'basis': w['basis'], 'nao': nao,
-                   'path': '4-center direct J/K (hermi=1, with_j, with_k)', 'direct_scf_tol': 1e-13,
-                   'dm': 'SCF-like 2*C_occ*C_occ^T, orthonormal random C_occ, seed 1', 'builds_per_step': world,
+        'higher_is_better': False, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'molecule': w['geom'], 'basis': w['basis'], 'nao': nao, 'path': path,
+                   'direct_scf_tol': 1e-13, 'dm': 'SCF-like 2*C_occ*C_occ^T, orthonormal random C_occ, seed 1',
                    'l2_flush': '256 MiB memset between steps, outside the per-step CUDA-event pairs',
-                   'parallelism': 'replicas' if world > 1 else 'single'},
-        'e2e': {'value': e2e_ms_mean * 1e-3, 'unit': 's', 'h2d_bytes_per_step': int(nao * nao * 8),
-                'd2h_bytes_per_step': int(2 * nao * nao * 8), 'api': 'pyscf_b200.jk.VHFOpt.get_jk (pinned host dm)'},
+                   'parallelism': ('one build sharded over %d GPUs + 1 NCCL all-reduce of [J;K]' % world) if world > 1 else 'single GPU'},
+        'e2e': {'value': e2e_ms_mean * 1e-3, 'unit': 's', 'h2d_bytes_per_step': int(nao * nao * 8 + (nao * w['nocc'] * 8 if is_df else 0)),
+                'd2h_bytes_per_step': int(2 * nao * nao * 8),
+                'api': 'pyscf_b200.df.DF.get_jk' if is_df else 'pyscf_b200.jk.VHFOpt.get_jk (pinned host dm)'},
         'gpu_launches': int(launches), 'setup_s': setup_s, 'clocks': clocks, 'roofline': roof,
-        'wall_s_timed_region': t_wall, 'quartets_computed': h.stats()['quartets_computed'],
-        'quartets_screened': h.stats()['quartets_screened'],
+        'wall_s_timed_region': t_wall,
+        'device_vs_public_max_abs': float(max(abs(vj - vj_dev).max(), abs(vk - vk_dev).max())),
     }
+    if not is_df:
+        out['quartets_computed'] = h.stats()['quartets_computed']
+        out['quartets_screened'] = h.stats()['quartets_screened']
     if cpu is not None:
         out['cpu_baseline'] = cpu
     print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+
+
+def cpu_baseline_df(mol, dm, c_occ, workload):
+    """Reference DF J/K algebra (df_jk.get_jk, pyscf/df/df_jk.py:362-380: dsymm-like half transform + dgemm) in numpy/OpenBLAS
+    on a bounded sample of auxiliary rows of a random surrogate tensor of the right shape (timing only), scaled to naux."""
+    from pyscf_b200.gto.mole import make_auxmol
+    ncores = os.cpu_count() or 1
+    aux = make_auxmol(mol)
+    naux, nao = aux.nao, mol.nao
+    nocc = c_occ.shape[1]
+    rows = max(8, min(naux, int(2e9 / (nao * nao * 8))))   # <= 2 GB sample
+    rng = np.random.RandomState(0)
+    eri1 = rng.standard_normal((rows, nao, nao))
+    orbo = np.asfortranarray(c_occ * np.sqrt(2.0))
+    dmtril = rng.standard_normal(nao * (nao + 1) // 2)
+    packed = rng.standard_normal((rows, nao * (nao + 1) // 2))
+    t = time.perf_counter()
+    vj = dmtril.dot(packed.T).dot(packed)
+    buf = np.einsum('pij,jk->pki', eri1, orbo, optimize=True) if False else np.matmul(eri1, orbo)   # (P, nao, nocc)
+    buf = buf.transpose(0, 2, 1).reshape(-1, nao)
+    vk = buf.T.dot(buf)
+    dt = (time.perf_counter() - t) * naux / rows
+    model = ''
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.startswith('model name'):
+                model = line.split(':', 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return {'value': dt, 'unit': 's', 'cores': ncores, 'kind': 'port',
+            'sample': '%d of %d auxiliary rows of %s (reference algebra df_jk.py:362-380 on a random tensor of the same shape: '
+                      'two GEMV for J, batched matmul + GEMM for K, numpy/OpenBLAS all cores), time scaled by naux/rows'
+                      % (rows, naux, workload), 'cpu_model': model}
 
 
 def cpu_baseline(mol, dm, workload, keep=True):
@@ -270,7 +368,12 @@ def run_reference(args, rank, world):
     times = []
     base = None
     for k in range(args.warmup + args.steps):
-        base = cpu_baseline(mol, dm, args.workload, keep=False)
+        if w['kind'] == 'df':
+            rng = np.random.RandomState(1)
+            c_occ, _ = np.linalg.qr(rng.standard_normal((mol.nao, w['nocc'])))
+            base = cpu_baseline_df(mol, dm, c_occ, args.workload)
+        else:
+            base = cpu_baseline(mol, dm, args.workload, keep=False)
         if k >= args.warmup:
             times.append(base['value'])
     v = float(np.mean(times))
@@ -279,7 +382,7 @@ def run_reference(args, rank, world):
            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': v * 1e3, 'higher_is_better': False,
            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
            'config': {'workload': args.workload, 'molecule': w['geom'], 'basis': w['basis'], 'nao': mol.nao,
-                      'path': '4-center direct J/K (hermi=1)', 'direct_scf_tol': 1e-13,
+                      'path': ('DF J/K' if w['kind'] == 'df' else '4-center direct J/K (hermi=1)'), 'direct_scf_tol': 1e-13,
                       'note': 'reference CPU path = oracle port (libcint is not vendored in the reference tree; '
                               'see DESIGN.md)'},
            'cpu_baseline': base,

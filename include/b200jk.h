@@ -71,6 +71,9 @@ int b200jk_df_build(b200jk_handle h, const int32_t* aux_atm, int aux_natm, const
 int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao, const double* occ_coeff, int nocc, int hermi,
                  double* vj, double* vk);
 int b200jk_df_naux(b200jk_handle h, int* naux);
+/* b200jk_df_jk with dm, occ_coeff, vj, vk already on the handle's device (device pointers, no host copies). */
+int b200jk_df_jk_device(b200jk_handle h, const double* dm_dev, int n_dm, int nao, const double* occ_dev, int nocc, int hermi,
+                        double* vj_dev, double* vk_dev);
 /* K-build engine for the occupied-orbital path: mode 1 (default) = tcgen05 int8-slice GEMMs (i8gemm.cuh) with
  * `nslices` 7-bit slices (7 -> ~1e-11 relative), mode 0 = cuBLAS DGEMM on the FP64 pipe (kept as yardstick). */
 int b200jk_df_set_kmode(b200jk_handle h, int mode, int nslices);
@@ -81,6 +84,11 @@ int b200jk_df_get_cderi(b200jk_handle h, double* out, int r0, int nr);
 /* Schwarz table q_cond[nbas,nbas] in the reference's (contracted, spherical-order) shell indexing. */
 int b200jk_get_q_cond(b200jk_handle h, double* q_cond, int nbas);
 
+/* Multi-GPU partition (one process per GPU): this handle computes only its share of the work — bra shell
+ * pairs i*world+rank of every class on the 4-center path, auxiliary rows [naux*rank/world, naux*(rank+1)/world)
+ * on the DF path — and returns PARTIAL J/K; the caller sums them with one all-reduce (NCCL) per build.
+ * The reference analogue is the OpenMP work split + critical-section reduction, pyscf/lib/vhf/nr_direct.c:429-482. */
+int b200jk_set_shard(b200jk_handle h, int rank, int world);
 /* Run all work of this handle on the caller's CUDA stream (cudaStream_t cast to void*); NULL restores the
  * handle's own stream.  Lets a host framework (e.g. torch) order and time the calls with its own events. */
 int b200jk_set_stream(b200jk_handle h, void* cuda_stream);

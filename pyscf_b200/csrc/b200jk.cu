@@ -306,6 +306,7 @@ static int direct_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, 
         P.dmj = h->d_dmj; P.dmk = dmk; P.vj = vj ? h->d_vj : nullptr; P.vk = vk ? h->d_vk : nullptr;
         P.n = h->ncart; P.n_dm_j = n_dm; P.n_dm_k = n_dm_k;
         P.counters = h->d_counters;
+        P.shard_rank = h->shard_rank; P.shard_world = h->shard_world;
 #ifndef B200JK_EMULATE
         CK(cudaEventRecord(h->ev0, st));
 #endif
@@ -411,6 +412,13 @@ extern "C" int b200jk_get_class_times(b200jk_handle h, double* ms, int n)
 {
     if (!h || !ms || n != NPC * NPC) return 1;
     memcpy(ms, h->class_ms, sizeof(double) * n);
+    return 0;
+}
+
+extern "C" int b200jk_set_shard(b200jk_handle h, int rank, int world)
+{
+    if (!h || world < 1 || rank < 0 || rank >= world) { set_err(h, "bad shard"); return 1; }
+    h->shard_rank = rank; h->shard_world = world;
     return 0;
 }
 

@@ -61,7 +61,7 @@ struct DFState {
     cublasHandle_t cublas = nullptr;
     cusolverDnHandle_t cusolver = nullptr;
     i8g::SliceStack SA, SC, SY;
-    bool sa_persistent = false; int sa_ns = 0;   // slices of the whole unpacked tensor kept resident (memory permitting)
+    bool sa_persistent = false; int sa_ns = 0, sa_lo = 0, sa_hi = 0;   // slices of the whole unpacked tensor kept resident (memory permitting)
 #endif
 };
 
@@ -535,8 +535,8 @@ extern "C" int b200jk_df_get_cderi(b200jk_handle h, double* out, int r0, int nr)
     return 0;
 }
 
-extern "C" int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao, const double* occ, int nocc, int hermi,
-                            double* vj, double* vk)
+static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, const double* occ, int nocc, int hermi,
+                      double* vj, double* vk, bool on_device)
 {
     if (!h) return 1;
     try {
@@ -548,6 +548,8 @@ extern "C" int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao
         auto t0 = std::chrono::steady_clock::now();
         const long npair = d->npair, n2 = (long)nao * nao;
         const int naux = d->naux;
+        // multi-GPU: this rank contracts only its auxiliary rows [r_lo, r_hi) and returns partial J/K
+        const int r_lo = (int)((long)naux * h->shard_rank / h->shard_world), r_hi = (int)((long)naux * (h->shard_rank + 1) / h->shard_world);
 #ifndef B200JK_EMULATE
         CK(cudaSetDevice(h->device));
         cudaStream_t st = h->stream;
@@ -568,7 +570,12 @@ extern "C" int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao
             d->d_vj = (double*)dev_alloc((size_t)n_dm * n2 * 8);
             d->ws_ndm = n_dm;
         }
-        h2d(d->d_dm, dm, (size_t)n_dm * n2 * 8, st);
+        if (!on_device) h2d(d->d_dm, dm, (size_t)n_dm * n2 * 8, st);
+        else {
+#ifndef B200JK_EMULATE
+            CK(cudaMemcpyAsync(d->d_dm, dm, (size_t)n_dm * n2 * 8, cudaMemcpyDeviceToDevice, st));
+#endif
+        }
         uint64_t launches = 0;
 #ifndef B200JK_EMULATE
         CK(cudaEventRecord(h->ev0, st));
@@ -583,17 +590,17 @@ extern "C" int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao
             const unsigned nseg = (unsigned)((npair + seglen - 1) / seglen);
             // two streaming passes over the tensor (rho, then J): 2 launches, both HBM-bound
             (void)rb;
-            for (int r0 = 0; r0 < naux; r0 += 32768) {
-                int nr = std::min(32768, naux - r0);
+            for (int r0 = r_lo; r0 < r_hi; r0 += 32768) {
+                int nr = std::min(32768, r_hi - r0);
                 dfj_rho_kernel<<<dim3(nseg, nr, n_dm), 256, 0, st>>>(d->d_cderi, d->d_dmtril, d->d_rho, npair, r0, naux, seglen);
                 launches++;
             }
-            dfj_acc_kernel<<<(unsigned)((npair + 255) / 256), 256, 0, st>>>(d->d_cderi, d->d_rho, d->d_vjtril, npair, 0, naux, naux, n_dm);
+            dfj_acc_kernel<<<(unsigned)((npair + 255) / 256), 256, 0, st>>>(d->d_cderi, d->d_rho, d->d_vjtril, npair, r_lo, r_hi - r_lo, naux, n_dm);
             launches++;
             CK(cudaGetLastError());
 #else
             for (int s = 0; s < n_dm; s++)
-                for (int r = 0; r < naux; r++) {
+                for (int r = r_lo; r < r_hi; r++) {
                     double acc = 0;
                     for (long t = 0; t < npair; t++) acc += d->d_cderi[(size_t)r * npair + t] * d->d_dmtril[(size_t)s * npair + t];
                     for (long t = 0; t < npair; t++) d->d_vjtril[(size_t)s * npair + t] += acc * d->d_cderi[(size_t)r * npair + t];
@@ -601,7 +608,12 @@ extern "C" int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao
 #endif
             UnpackTrilFn uf{d->d_vjtril, d->d_vj, nao, npair};
             launch_1d((long)n_dm * n2, uf, st); launches++;
-            d2h(vj, d->d_vj, (size_t)n_dm * n2 * 8, st);
+            if (!on_device) d2h(vj, d->d_vj, (size_t)n_dm * n2 * 8, st);
+            else {
+#ifndef B200JK_EMULATE
+                CK(cudaMemcpyAsync(vj, d->d_vj, (size_t)n_dm * n2 * 8, cudaMemcpyDeviceToDevice, st));
+#endif
+            }
         }
         if (vk) {
             bool use_occ = (occ != nullptr && nocc > 0);
@@ -613,7 +625,14 @@ extern "C" int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao
                 d->d_occ = (double*)dev_alloc((size_t)n_dm * nao * ncol * 8);
                 d->ws_rows = kb; d->ws_nocc = ncol;
             }
-            if (use_occ) h2d(d->d_occ, occ, (size_t)n_dm * nao * nocc * 8, st);
+            if (use_occ) {
+                if (!on_device) h2d(d->d_occ, occ, (size_t)n_dm * nao * nocc * 8, st);
+                else {
+#ifndef B200JK_EMULATE
+                    CK(cudaMemcpyAsync(d->d_occ, occ, (size_t)n_dm * nao * nocc * 8, cudaMemcpyDeviceToDevice, st));
+#endif
+                }
+            }
             dev_zero(d->d_vk, (size_t)n_dm * n2 * 8, st);
 #ifndef B200JK_EMULATE
             const bool tc = use_occ && d->k_mode == 1;
@@ -626,29 +645,29 @@ extern "C" int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao
             }
 #endif
 #ifndef B200JK_EMULATE
-            if (tc && !(d->sa_persistent && d->sa_ns == d->k_slices)) {
+            if (tc && !(d->sa_persistent && d->sa_ns == d->k_slices && d->sa_lo == r_lo && d->sa_hi == r_hi)) {
                 // slice the whole unpacked tensor once and keep it (7 B per element) when it fits comfortably
                 size_t freeb = 0, totb = 0;
                 CK(cudaMemGetInfo(&freeb, &totb));
-                size_t rows_tot = (size_t)naux * nao, rp = ((rows_tot + 255) / 256) * 256, kp = ((size_t)nao + 127) / 128 * 128;
+                size_t rows_tot = (size_t)(r_hi - r_lo) * nao, rp = ((rows_tot + 255) / 256) * 256, kp = ((size_t)nao + 127) / 128 * 128;
                 size_t need = (size_t)d->k_slices * rp * kp;
                 d->sa_persistent = false;
                 if (need < freeb / 2 && rows_tot < (1u << 31)) {
                     d->SA.alloc((int)rows_tot, nao, d->k_slices);
                     CK(cudaMemsetAsync(d->SA.q, 0, need, st));
                     CK(cudaMemsetAsync(d->SA.E, 0, rp * 4, st));
-                    for (int r0 = 0; r0 < naux; r0 += kb) {
-                        int nr = std::min(kb, naux - r0);
+                    for (int r0 = r_lo; r0 < r_hi; r0 += kb) {
+                        int nr = std::min(kb, r_hi - r0);
                         UnpackFn up{d->d_cderi, d->d_A, nao, npair, r0};
                         launch_1d((long)nr * n2, up, st);
-                        i8g::split_rows_into(d->SA, r0 * nao, d->d_A, nao, nr * nao, st);
+                        i8g::split_rows_into(d->SA, (r0 - r_lo) * nao, d->d_A, nao, nr * nao, st);
                     }
-                    d->sa_persistent = true; d->sa_ns = d->k_slices;
+                    d->sa_persistent = true; d->sa_ns = d->k_slices; d->sa_lo = r_lo; d->sa_hi = r_hi;
                 }
             }
 #endif
-            for (int r0 = 0; r0 < naux; r0 += kb) {
-                int nr = std::min(kb, naux - r0);
+            for (int r0 = r_lo; r0 < r_hi; r0 += kb) {
+                int nr = std::min(kb, r_hi - r0);
 #ifndef B200JK_EMULATE
                 if (!(tc && d->sa_persistent)) {
                     UnpackFn up{d->d_cderi, d->d_A, nao, npair, r0};
@@ -664,7 +683,7 @@ extern "C" int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao
                     const double one = 1.0, zero = 0.0;
                     if (tc) {
                         // tcgen05 path: Y2[nu][(P,i)] = sum_mu A_P[nu,mu] Ct[i,mu] ; K += Y2 Y2^T (upper triangle)
-                        if (r0 == 0 || n_dm > 1) {
+                        if (r0 == r_lo || n_dm > 1) {
                             TransposeFn tr{d->d_occ + (size_t)s * nao * nocc, d->d_occT, nao, nocc};
                             launch_1d((long)nao * nocc, tr, st);
                             i8g::split_rows(d->SC, d->d_occT, nao, nocc, nao, d->k_slices, st); launches += 2;
@@ -681,13 +700,13 @@ extern "C" int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao
                         };
                         tick(-1);
                         tick(0);
-                        i8g::gemm_ar(d->SA, d->sa_persistent ? r0 * nao : 0, nr * nao, d->SC, d->d_Y2, (long)nr * nocc, nao, st);
+                        i8g::gemm_ar(d->SA, d->sa_persistent ? (r0 - r_lo) * nao : 0, nr * nao, d->SC, d->d_Y2, (long)nr * nocc, nao, st);
                         tick(1);
                         i8g::split_rows(d->SY, d->d_Y2, (long)nr * nocc, nao, nr * nocc, d->k_slices, st);
                         tick(2);
                         i8g::gemm(d->SY, d->SY, d->d_vk + (size_t)s * n2, nao, 0, true, st);
                         tick(3);
-                        if (prof && r0 + kb >= naux) {
+                        if (prof && r0 + kb >= r_hi) {
                             fprintf(stderr, "[df-k profile] zeroY2 %.2f ms, gemm1 %.2f ms, splitY %.2f ms, gemm2 %.2f ms (sum over blocks, kb=%d)\n",
                                     tacc[0], tacc[1], tacc[2], tacc[3], kb);
                             for (double& t : tacc) t = 0;
@@ -737,7 +756,12 @@ extern "C" int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao
 #ifndef B200JK_EMULATE
             if (use_occ && d->k_mode == 1) { MirrorUpperFn mf{d->d_vk, nao}; for (int s = 0; s < n_dm; s++) { mf.a = d->d_vk + (size_t)s * n2; launch_1d(n2, mf, st); launches++; } }
 #endif
-            d2h(vk, d->d_vk, (size_t)n_dm * n2 * 8, st);
+            if (!on_device) d2h(vk, d->d_vk, (size_t)n_dm * n2 * 8, st);
+            else {
+#ifndef B200JK_EMULATE
+                CK(cudaMemcpyAsync(vk, d->d_vk, (size_t)n_dm * n2 * 8, cudaMemcpyDeviceToDevice, st));
+#endif
+            }
         }
 #ifndef B200JK_EMULATE
         CK(cudaEventRecord(h->ev1, st));
@@ -751,6 +775,18 @@ extern "C" int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao
         h->stats.kernel_launches = launches;
     } catch (std::exception& e) { set_err(h, e.what()); return 2; }
     return 0;
+}
+
+extern "C" int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao, const double* occ, int nocc, int hermi,
+                            double* vj, double* vk)
+{
+    return df_jk_impl(h, dm, n_dm, nao, occ, nocc, hermi, vj, vk, false);
+}
+// same with dm / occ_coeff / vj / vk resident on the device (multi-GPU all-reduce, HBM-resident benchmark)
+extern "C" int b200jk_df_jk_device(b200jk_handle h, const double* dm, int n_dm, int nao, const double* occ, int nocc, int hermi,
+                                   double* vj, double* vk)
+{
+    return df_jk_impl(h, dm, n_dm, nao, occ, nocc, hermi, vj, vk, true);
 }
 
 extern "C" int b200jk_df_set_kmode(b200jk_handle h, int mode, int nslices)

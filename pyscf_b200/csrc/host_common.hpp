@@ -176,6 +176,7 @@ struct b200jk_handle_s {
     cudaEvent_t ev_in = nullptr;
 #endif
     int profile = 0;
+    int shard_rank = 0, shard_world = 1;   // multi-GPU work partition (b200jk_set_shard)
     DFState* df = nullptr;          // density-fitting state (df.cu)
     void (*df_free)(DFState*) = nullptr;
     double class_ms[NPC * NPC] = {0};

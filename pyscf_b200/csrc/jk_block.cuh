@@ -28,6 +28,7 @@ struct KParams {
     int n, n_dm_j, n_dm_k;
     int kchunk;
     int bra_nprim_max;
+    int shard_rank, shard_world;   // multi-GPU: this rank owns bra pairs bx = i*world + rank (lists are cost-sorted)
     unsigned long long* counters;  // [0] quartets computed, [1] quartets screened out (may be null)
 };
 

@@ -52,14 +52,16 @@ struct ClassCfg {
 template <class C>
 __global__ void __launch_bounds__(TpqCfg<C>::NT) jk_tpq_kernel(const KParams P)
 {
-    tpq_block<C>(P, blockIdx.x, blockIdx.y, blockIdx.z);
+    const int bx = blockIdx.x * P.shard_world + P.shard_rank;
+    if (bx < P.nbra) tpq_block<C>(P, bx, blockIdx.y, blockIdx.z);
 }
 template <class C>
 __global__ void __launch_bounds__(GroupCfg<C>::NT) jk_class_kernel(const KParams P)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     BlockSmem<C>& sm = *reinterpret_cast<BlockSmem<C>*>(smraw);
-    jk_block<C>(P, blockIdx.x, blockIdx.y, sm);
+    const int bx = blockIdx.x * P.shard_world + P.shard_rank;
+    if (bx < P.nbra) jk_block<C>(P, bx, blockIdx.y, sm);
 }
 #endif
 
@@ -76,22 +78,24 @@ void launch_one(KParams P, b2_stream_t st)
     using C = typename Cfg::C;
     if constexpr (TpqCfg<C>::eligible) {
         // low angular momentum: one thread per quartet, registers only (jk_tpq.cuh)
-        P.kchunk = pick_kchunk(P.nbra, P.nket, TpqCfg<C>::NT, TpqCfg<C>::KCHUNK);
+        const int nbx = (P.nbra + P.shard_world - 1) / P.shard_world;   // bra pairs of this rank
+        P.kchunk = pick_kchunk(nbx, P.nket, TpqCfg<C>::NT, TpqCfg<C>::KCHUNK);
         int ny = (P.nket + P.kchunk - 1) / P.kchunk;
 #ifndef B200JK_EMULATE
-        dim3 grid(P.nbra, ny, (P.bra_nprim_max + TpqCfg<C>::PSLICE - 1) / TpqCfg<C>::PSLICE);
+        dim3 grid(nbx, ny, (P.bra_nprim_max + TpqCfg<C>::PSLICE - 1) / TpqCfg<C>::PSLICE);
         jk_tpq_kernel<C><<<grid, TpqCfg<C>::NT, 0, st>>>(P);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) throw std::runtime_error(std::string("jk_tpq_kernel launch: ") + cudaGetErrorString(e));
 #else
         (void)st;
-        for (int bx = 0; bx < P.nbra; bx++)
+        for (int bx = P.shard_rank; bx < P.nbra; bx += P.shard_world)
             for (int by = 0; by < ny; by++)
                 for (int bz = 0; bz * TpqCfg<C>::PSLICE < P.bra_nprim_max; bz++) tpq_block<C>(P, bx, by, bz);
 #endif
         return;
     }
-    P.kchunk = pick_kchunk(P.nbra, P.nket, Cfg::GC::NSLOT, KCH_MAX);
+    const int nbx = (P.nbra + P.shard_world - 1) / P.shard_world;
+    P.kchunk = pick_kchunk(nbx, P.nket, Cfg::GC::NSLOT, KCH_MAX);
     int ny = (P.nket + P.kchunk - 1) / P.kchunk;
 #ifndef B200JK_EMULATE
     static bool configured = false;
@@ -101,14 +105,14 @@ void launch_one(KParams P, b2_stream_t st)
         if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
         configured = true;
     }
-    dim3 grid(P.nbra, ny);
+    dim3 grid(nbx, ny);
     jk_class_kernel<C><<<grid, Cfg::NT, smem, st>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("jk_class_kernel launch: ") + cudaGetErrorString(e));
 #else
     (void)st;
     BlockSmem<C>* sm = new BlockSmem<C>();
-    for (int bx = 0; bx < P.nbra; bx++)
+    for (int bx = P.shard_rank; bx < P.nbra; bx += P.shard_world)
         for (int by = 0; by < ny; by++) jk_block<C>(P, bx, by, *sm);
     delete sm;
 #endif

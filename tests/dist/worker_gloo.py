@@ -1,0 +1,43 @@
+"""world_size-2 gloo worker: sharded J/K through the CPU emulation library equals the unsharded oracle."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch.distributed as dist
+
+from pyscf_b200 import gto
+from pyscf_b200.df import DF, TaggedDM
+from pyscf_b200.jk import VHFOpt
+from pyscf_b200.parallel import ShardedJK
+from pyscf_b200.gto.mole import make_auxmol
+from oracle import oracle as O
+
+emu = sys.argv[1]
+dist.init_process_group('gloo')
+rank = dist.get_rank()
+mol = gto.M(atom='O 0 0 0; H 0 -0.757 0.587; H 0 0.757 0.587', basis='cc-pvdz')
+nao = mol.nao
+np.random.seed(1)
+dm = np.random.random((nao, nao))
+dm = dm + dm.T
+# 4-center path
+sj = ShardedJK(VHFOpt(mol, libpath=emu))
+vj, vk = sj.get_jk(dm, hermi=1)
+rj, rk = O.get_jk(mol, dm)
+assert abs(vj - rj).max() < 1e-10 and abs(vk - rk).max() < 1e-10, (abs(vj - rj).max(), abs(vk - rk).max())
+# partial results really are partial (each rank did only part of the work)
+pj, pk = sj.engine.get_jk(dm, hermi=1)
+assert abs(pj - rj).max() > 1e-3
+# DF path
+dfobj = DF(mol, 'weigend', libpath=emu).build()
+sd = ShardedJK(dfobj)
+ref, _ = O.cholesky_eri(mol, make_auxmol(mol, 'weigend'))
+vj, vk = sd.get_jk(dm)
+rj, rk = O.df_get_jk(ref, nao, dm)
+assert abs(vj - rj).max() < 1e-10 and abs(vk - rk).max() < 1e-10
+dist.barrier()
+if rank == 0:
+    print('GLOO_SHARD_OK')
+dist.destroy_process_group()
