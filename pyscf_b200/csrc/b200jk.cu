@@ -116,10 +116,14 @@ extern "C" int b200jk_create(b200jk_handle* out, const int32_t* atm, int natm, c
             size_t nd = b200jk_rys_blob_size / 8;
             if ((int)blob[0] != RYS_NMAX || (int)blob[1] != RYS_DEG || (int)blob[2] != RYS_NINT)
                 throw std::runtime_error("rys table header mismatch");
-            h->d_rys = (double*)dev_alloc(nd * 8);
-            h2d(h->d_rys, blob, nd * 8);
-            h->tb.herm = h->d_rys + 5;
-            h->tb.cheb = h->d_rys + 5 + RYS_NMAX * (RYS_NMAX + 1);
+            // device layout: [hermite (NMAX(NMAX+1) doubles)] [pad] [chebyshev rows, 32-byte aligned for 256-bit loads]
+            const size_t nherm = RYS_NMAX * (RYS_NMAX + 1), ncheb = nd - 5 - nherm;
+            const size_t cheb_off = (nherm + 3) / 4 * 4;
+            h->d_rys = (double*)dev_alloc((cheb_off + ncheb) * 8);
+            h2d(h->d_rys, blob + 5, nherm * 8);
+            h2d(h->d_rys + cheb_off, blob + 5 + nherm, ncheb * 8);
+            h->tb.herm = h->d_rys;
+            h->tb.cheb = h->d_rys + cheb_off;
         }
 
         // ---- shell pairs and primitive pairs per class
@@ -219,8 +223,20 @@ extern "C" int b200jk_set_screening(b200jk_handle h, double tol, double omega)
             P.kept.clear();
             // a pair can only survive q_ij*q_kl > tol if q_ij*qmax > tol (density factors <= O(1) are
             // applied per quartet on device; keep the Schwarz-only bound here, like q_cond in the reference)
-            for (auto& sp : P.all)
-                if (sp.q * qmax > tol * 1e-2) P.kept.push_back(sp);
+            // Deeply contracted pairs are split into sub-pairs of <= MAX_PRIM_PER_PAIR primitive pairs (same shells, same
+            // AO block, consecutive primitive ranges).  Integrals are linear in the primitive sum and the unique-quartet
+            // rule works on list positions, so (a+b|a+b)/2 = (a|a)/2 + (b|a) + (b|b)/2 is reproduced exactly; it bounds
+            // the serial primitive loop of one thread/group (4096 -> 256 for the C 1s x C 1s pairs).
+            constexpr int MAX_PRIM_PER_PAIR = 16;
+            for (auto& sp : P.all) {
+                if (!(sp.q * qmax > tol * 1e-2)) continue;
+                for (int p0 = 0; p0 < sp.nprim; p0 += MAX_PRIM_PER_PAIR) {
+                    ShellPair sub = sp;
+                    sub.prim_off = sp.prim_off + p0;
+                    sub.nprim = std::min(MAX_PRIM_PER_PAIR, sp.nprim - p0);
+                    P.kept.push_back(sub);
+                }
+            }
             // batches of kets are homogeneous in primitive count (groups iterate to the longest slot), then by bound
             std::stable_sort(P.kept.begin(), P.kept.end(), [](const ShellPair& a, const ShellPair& b) {
                 return a.nprim != b.nprim ? a.nprim > b.nprim : a.q > b.q; });
@@ -334,6 +350,7 @@ static int direct_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, 
             P.ket_pairs = K.d_kept; P.nket = (int)K.kept.size();
             P.same_class = (cb == ck);
             P.bra_nprim_max = B.kept[0].nprim;  // kept lists are sorted by primitive count, largest first
+            P.ket_nprim_max = K.kept[0].nprim;
 #ifndef B200JK_EMULATE
             cudaStream_t ss = h->profile ? st : h->side[jn % h->side.size()];
             if (h->profile) {

@@ -27,7 +27,7 @@ struct KParams {
     double* vj; double* vk;
     int n, n_dm_j, n_dm_k;
     int kchunk;
-    int bra_nprim_max;
+    int bra_nprim_max, ket_nprim_max;
     int shard_rank, shard_world;   // multi-GPU: this rank owns bra pairs bx = i*world + rank (lists are cost-sorted)
     unsigned long long* counters;  // [0] quartets computed, [1] quartets screened out (may be null)
 };

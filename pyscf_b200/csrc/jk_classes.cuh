@@ -122,6 +122,14 @@ void launch_one(KParams P, b2_stream_t st)
 #define B2_PAIR_CASES(X) \
     X(0, 0, 0) X(1, 1, 0) X(2, 1, 1) X(3, 2, 0) X(4, 2, 1) X(5, 2, 2) X(6, 3, 0) X(7, 3, 1) X(8, 3, 2) X(9, 3, 3)
 
+// Orientation of a class pair (hi id > lo id): by default the larger class is the register-resident bra.  For these
+// pairs the opposite choice packs the warps better (threads = fs/fp components instead of dp/dd: 30 of 32 lanes
+// instead of 18) and needs fewer reductions per integral, so they run with bra = lo class, ket = hi class.
+constexpr bool use_swapped(int hi, int lo)
+{
+    return (hi == 6 && lo == 4) || (hi == 7 && lo == 4) || (hi == 6 && lo == 2) || (hi == 7 && lo == 5);
+}
+
 template <int LI, int LJ>
 void launch_ket(int ck, const KParams& P, b2_stream_t st)
 {
@@ -129,7 +137,7 @@ void launch_ket(int ck, const KParams& P, b2_stream_t st)
     switch (ck) {
 #define X(id, lk, ll)                                                      \
     case id:                                                               \
-        if constexpr (id <= cb) launch_one<LI, LJ, lk, ll>(P, st);         \
+        if constexpr (id <= cb || use_swapped(id, cb)) launch_one<LI, LJ, lk, ll>(P, st); \
         return;
         B2_PAIR_CASES(X)
 #undef X
@@ -142,8 +150,15 @@ void launch_ket(int ck, const KParams& P, b2_stream_t st)
 B2_PAIR_CASES(X)
 #undef X
 
-inline void launch_class(int cb, int ck, const KParams& P, b2_stream_t st)
+inline void launch_class(int cb, int ck, const KParams& P0, b2_stream_t st)
 {
+    KParams P = P0;
+    if (cb > ck && use_swapped(cb, ck)) {   // run the pair with the smaller class as the stationary bra
+        P.bra_pairs = P0.ket_pairs; P.nbra = P0.nket;
+        P.ket_pairs = P0.bra_pairs; P.nket = P0.nbra;
+        P.bra_nprim_max = P0.ket_nprim_max; P.ket_nprim_max = P0.bra_nprim_max;
+        int t = cb; cb = ck; ck = t;
+    }
     switch (cb) {
 #define X(id, li, lj)                  \
     case id:                           \

@@ -78,7 +78,18 @@ B2_HD void rys_root(const RysTables& tb, int n, int r, double x, double& u, doub
     int iv = (int)(x * (1.0 / RYS_H));
     if (iv > RYS_NINT - 1) iv = RYS_NINT - 1;
     double t = (x - iv * RYS_H) * (2.0 / RYS_H) - 1.0;
-    const double* c = tb.cheb + (size_t)RYS_NINT * 28 * (n * (n - 1) / 2) + (size_t)(iv * n + r) * 28;
+    const double* cp = tb.cheb + (size_t)RYS_NINT * 28 * (n * (n - 1) / 2) + (size_t)(iv * n + r) * 28;
+    double c[28];
+#if defined(__CUDA_ARCH__)
+    // one table row = 224 B = 7 x 256-bit loads (LDG.E.256 on sm_100a); rows are 32-byte aligned (b200jk_create)
+    B2_UNROLL
+    for (int j = 0; j < 7; j++)
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(c[4 * j]), "=d"(c[4 * j + 1]), "=d"(c[4 * j + 2]), "=d"(c[4 * j + 3])
+                     : "l"(cp + 4 * j));
+#else
+    for (int j = 0; j < 28; j++) c[j] = cp[j];
+#endif
     double t2 = 2.0 * t, b1 = 0.0, b2 = 0.0, d1 = 0.0, d2 = 0.0;
     B2_UNROLL
     for (int j = RYS_DEG; j >= 1; j--) {
