@@ -336,11 +336,23 @@ def cpu_baseline_df(mol, dm, c_occ, workload):
 
 
 def cpu_baseline(mol, dm, workload, keep=True):
+    """4-center CPU arm: the reference's own CVHFnr_direct_drv + nrs8 digestion + CVHFnrs8_prescreen compiled from the
+    reference sources (oracle/_ref, kind "reference") when present, else the oracle's restatement (kind "port").
+    Either way the integral function is oracle_cint.c's int2e_sph — libcint is not vendored in the reference tree."""
     from oracle import oracle as O
+    from oracle import ref_driver as R
     ncores = os.cpu_count() or 1
     os.environ.setdefault('OMP_NUM_THREADS', str(ncores))
     t = time.perf_counter()
-    vj, vk, nq = O.get_jk(mol, dm, return_count=True)
+    if R.available():
+        vj, vk = R.get_jk(mol, dm, hermi=1)
+        kind, nq = 'reference', None
+        what = ('reference driver/screening/digestion (pyscf/lib/vhf/nr_direct.c, nr_direct_dot.c, optimizer.c compiled in '
+                'place) + oracle McMurchie-Davidson int2e_sph (libcint absent)')
+    else:
+        vj, vk, nq = O.get_jk(mol, dm, return_count=True)
+        kind = 'port'
+        what = 'oracle McMurchie-Davidson integrals + s8 digestion restatement, OpenMP over shell pairs'
     dt = time.perf_counter() - t
     model = ''
     try:
@@ -350,10 +362,8 @@ def cpu_baseline(mol, dm, workload, keep=True):
                 break
     except Exception:
         pass
-    out = {'value': dt, 'unit': 's', 'cores': ncores, 'kind': 'port',
-           'sample': 'one full J/K build of %s (all %d screened shell quartets), oracle McMurchie-Davidson '
-                     'integrals + s8 digestion, OpenMP over shell pairs' % (workload, nq),
-           'cpu_model': model}
+    out = {'value': dt, 'unit': 's', 'cores': ncores, 'kind': kind,
+           'sample': 'one full J/K build of %s (every screened shell quartet), %s' % (workload, what), 'cpu_model': model}
     if keep:
         out['vj'], out['vk'] = vj, vk
     return out

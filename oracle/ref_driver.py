@@ -1,0 +1,96 @@
+"""The REFERENCE's own direct-SCF driver, screening and J/K digestion (compiled from the reference's C sources
+where they lie, oracle/Makefile.ref -> oracle/_ref/libcvhf_ref.so), fed with this oracle's integral function.
+
+TEST INFRASTRUCTURE ONLY.  Mirrors the call sequence of pyscf/scf/_vhf.py:151-206 (`_VHFOpt.init_cvhf_direct`),
+:224-244 (`set_dm`), :370-429 (`direct`) and :505-604 (`nr_direct_drv`): scripts 'ji->s2kl' + 'li->s2kj' (hermi=1)
+or 'li->s1kj' (hermi=0), `CVHFdot_nrs8`, `CVHFnrs8_prescreen`, then lib.hermi_triu.  libcint itself is absent, so the
+`intor` function pointer is oracle_cint.c's `int2e_sph`; everything else executed here is reference code.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import oracle as O
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATH = os.path.join(_HERE, '_ref', 'libcvhf_ref.so')
+_lib = None
+
+
+class CVHFOpt(ctypes.Structure):   # pyscf/lib/vhf/optimizer.h:23-35, pyscf/scf/_vhf.py:267-275
+    _fields_ = [('nbas', ctypes.c_int), ('ngrids', ctypes.c_int), ('direct_scf_cutoff', ctypes.c_double),
+                ('q_cond', ctypes.c_void_p), ('dm_cond', ctypes.c_void_p), ('fprescreen', ctypes.c_void_p),
+                ('r_vkscreen', ctypes.c_void_p)]
+
+
+def available():
+    return os.path.exists(_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(_PATH)
+    return _lib
+
+
+def _fptr(cdll, name):
+    return ctypes.c_void_p(ctypes.cast(getattr(cdll, name), ctypes.c_void_p).value)
+
+
+def get_jk(mol, dm, hermi=1, direct_scf_tol=1e-13, omega=None, screen=True):
+    """J, K through CVHFnr_direct_drv (reference C) for real dm [..., nao, nao]."""
+    ref, orc = lib(), O.lib()
+    atm = np.ascontiguousarray(mol._atm, dtype=np.int32)
+    bas = np.ascontiguousarray(mol._bas, dtype=np.int32)
+    env = np.array(mol._env, dtype=np.float64)
+    env[8] = 0.0 if omega is None else omega
+    natm, nbas = ctypes.c_int(len(atm)), ctypes.c_int(len(bas))
+    ao_loc = np.ascontiguousarray(mol.ao_loc_nr(cart=False), dtype=np.int32)
+    nao = int(ao_loc[-1])
+    dm = np.asarray(dm, dtype=np.float64)
+    shape = dm.shape
+    dms = np.ascontiguousarray(dm.reshape(-1, nao, nao))
+    n_dm = len(dms)
+    intor = _fptr(orc, 'int2e_sph')
+
+    opt = None
+    if screen:
+        q_cond = np.empty((len(bas), len(bas)))
+        ref.CVHFnr_int2e_q_cond(intor, None, q_cond.ctypes.data_as(ctypes.c_void_p), ao_loc.ctypes.data_as(ctypes.c_void_p),
+                                atm.ctypes.data_as(ctypes.c_void_p), natm, bas.ctypes.data_as(ctypes.c_void_p), nbas,
+                                env.ctypes.data_as(ctypes.c_void_p))
+        dm_cond = np.empty((len(bas), len(bas)))
+        ref.CVHFnr_dm_cond(dm_cond.ctypes.data_as(ctypes.c_void_p), dms.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(n_dm),
+                           ao_loc.ctypes.data_as(ctypes.c_void_p), atm.ctypes.data_as(ctypes.c_void_p), natm,
+                           bas.ctypes.data_as(ctypes.c_void_p), nbas, env.ctypes.data_as(ctypes.c_void_p))
+        opt = CVHFOpt(len(bas), 0, direct_scf_tol, q_cond.ctypes.data, dm_cond.ctypes.data,
+                      _fptr(ref, 'CVHFnrs8_prescreen').value, None)
+
+    kname = 'CVHFnrs8_li_s2kj' if hermi == 1 else 'CVHFnrs8_li_s1kj'
+    njk = 2 * n_dm
+    fjk = (ctypes.c_void_p * njk)()
+    dmptr = (ctypes.c_void_p * njk)()
+    vptr = (ctypes.c_void_p * njk)()
+    out = np.zeros((njk, nao, nao))
+    for i in range(n_dm):
+        fjk[i] = _fptr(ref, 'CVHFnrs8_ji_s2kl').value
+        fjk[n_dm + i] = _fptr(ref, kname).value
+        dmptr[i] = dmptr[n_dm + i] = dms[i].ctypes.data
+        vptr[i] = out[i].ctypes.data
+        vptr[n_dm + i] = out[n_dm + i].ctypes.data
+    shls_slice = (ctypes.c_int * 8)(*([0, len(bas)] * 4))
+    ref.CVHFnr_direct_drv(intor, _fptr(ref, 'CVHFdot_nrs8'), fjk, dmptr, vptr, ctypes.c_int(njk), ctypes.c_int(1), shls_slice,
+                          ao_loc.ctypes.data_as(ctypes.c_void_p), None, ctypes.byref(opt) if opt is not None else None,
+                          atm.ctypes.data_as(ctypes.c_void_p), natm, bas.ctypes.data_as(ctypes.c_void_p), nbas,
+                          env.ctypes.data_as(ctypes.c_void_p))
+    vj, vk = out[:n_dm], out[n_dm:]
+    # lib.hermi_triu (pyscf/lib/numpy_helper.py:499): fill the upper triangle from the lower one
+    il = np.tril_indices(nao, -1)
+    for v in vj:
+        v[il[1], il[0]] = v[il]
+    if hermi == 1:
+        for v in vk:
+            v[il[1], il[0]] = v[il]
+    return vj.reshape(shape), vk.reshape(shape)
