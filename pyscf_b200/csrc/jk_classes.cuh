@@ -16,7 +16,7 @@ constexpr int choose_np(int ni, int nj, int nkl)
     int nab = ni * nj;
     int best = 0, best_eff = -1;
     for (int np = 1; np <= nj; np++) {
-        if (nj % np != 0 || nab / np > 40) continue;
+        if (nj % np != 0 || nab / np > 30) continue;
         if (best && nab / np < 15) break;
         if (nkl * np > 512) break;
         int eff = lane_eff_permille(nkl * np);
@@ -103,6 +103,8 @@ void launch_one(KParams P, b2_stream_t st)
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(jk_class_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+        // leave half of the 228 KB for L1 (Rys tables, density blocks); the other half lets several CTAs co-reside
+        cudaFuncSetAttribute(jk_class_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
         configured = true;
     }
     dim3 grid(nbx, ny);

@@ -133,18 +133,22 @@ struct QClass {
     static constexpr int NR = (LI + LJ + LK + LL) / 2 + 1;
     static constexpr int LB = LI + LJ, LT = LK + LL, NB1 = LB + 1, NT1 = LT + 1, ISZ = NB1 * NT1;
     static constexpr int NI1 = LI + 1, NJ1 = LJ + 1;
-    static constexpr int ISP = ISZ | 1;   // padded (odd) stride of one I(n,m) array: conflict-free across tasks
+    static constexpr int GK = (LK + 1) * (LL + 1);      // ket (k,l) index pairs of the 2-D integrals
+    static constexpr int NB1P = (NB1 + 1) & ~1;           // bra length padded to an even count (16-byte rows)
+    static constexpr int HSZ = GK * NB1P;
+    static constexpr int HSP = HSZ + 2;                   // stride of one (direction, root) array: keeps 16-byte alignment
 };
 
 template <class C>
-struct SlotSmem {
-    double I[3][C::NR][C::ISP];  // VRR output I[n*NT1+m]; z carries weight*prefactor
+struct alignas(16) SlotSmem {
+    // 2-D integrals after the vertical recurrence AND the ket transfer (k -> l), ready for per-thread bra transfer:
+    // H[dir][root][(l*(LK+1)+k)*NB1P + n]; z carries weight*prefactor.  Rows of n are contiguous (LDS.128).
+    double H[3][C::NR][C::HSP];
     double U[C::NR], W[C::NR];
-    double pc[12];               // p, q, PA[3], QC[3], PQ[3], pad
+    double pc[14];               // p, q, PA[3], QC[3], PQ[3], 1/(p+q), 0.5/p, 0.5/q
     double ccd[3][C::LL + 1][C::LL + 1];  // binom(l,t) CD^(l-t)
     double fac;                  // symmetry factor (1, 1/2, 1/4, 1/8)
     int32_t kl, k0, l0, nprim_k, prim_off_k, active, pact, pad;
-    double pad_odd[((3 * C::NR * C::ISP + 2 * C::NR + 12 + 3 * (C::LL + 1) * (C::LL + 1) + 1 + 4) % 2 == 0) ? 1 : 2];  // odd slot stride
 };
 
 struct BraInfo {
@@ -222,16 +226,19 @@ B2_HD void phase_roots(SlotSmem<C>& s, int g, const PrimPair& bp, const PrimPair
         s.pc[5] = kp.PAx; s.pc[6] = kp.PAy; s.pc[7] = kp.PAz;
         s.pc[8] = PQx; s.pc[9] = PQy; s.pc[10] = PQz;
         s.pc[11] = ipq;
+        s.pc[12] = 0.5 / p; s.pc[13] = 0.5 / q;
     }
 }
 
-// Phase B: vertical recurrence for (root r, direction x) tasks g, g+G, ... < 3*NR
+// Phase B: tasks (root r, direction x) = g, g+G, ... < 3*NR: vertical recurrence in registers, then the ket transfer
+//   H(n; k,l) = sum_t binom(l,t) CD^(l-t) I(n, k+t)
+// so that phase D only loads one contiguous row of n per direction.
 template <class C>
 B2_HD void phase_vrr(SlotSmem<C>& s, int g)
 {
     double p = s.pc[0], q = s.pc[1];
     double ipq = s.pc[11];
-    double hip = 0.5 / p, hiq = 0.5 / q;
+    double hip = s.pc[12], hiq = s.pc[13];
     for (int task = g; task < 3 * C::NR; task += C::G) {
         int r = task / 3, x = task - 3 * r;
         double u = s.U[r];
@@ -240,45 +247,59 @@ B2_HD void phase_vrr(SlotSmem<C>& s, int g)
         double b01 = (1.0 - u * p * ipq) * hiq;
         double c00 = s.pc[2 + x] - u * q * ipq * s.pc[8 + x];
         double c0p = s.pc[5 + x] + u * p * ipq * s.pc[8 + x];
-        double* I = s.I[x][r];
-        constexpr int NT1 = C::NT1;
+        double I[C::NB1][C::NT1];
         double i0 = (x == 2) ? s.W[r] : 1.0;
-        I[0] = i0;
+        I[0][0] = i0;
         if (C::LB > 0) {
-            double im1 = i0, in = c00 * i0;
-            I[NT1] = in;
+            I[1][0] = c00 * i0;
             B2_UNROLL
-            for (int n = 1; n < C::LB; n++) {
-                double nx = c00 * in + n * b10 * im1;
-                I[(n + 1) * NT1] = nx;
-                im1 = in; in = nx;
-            }
+            for (int n = 1; n < C::LB; n++) I[n + 1][0] = c00 * I[n][0] + n * b10 * I[n - 1][0];
         }
         B2_UNROLL
         for (int m = 0; m < C::LT; m++) {
             B2_UNROLL
             for (int n = 0; n <= C::LB; n++) {
-                double val = c0p * I[n * NT1 + m];
-                if (m > 0) val += m * b01 * I[n * NT1 + m - 1];
-                if (n > 0) val += n * b00 * I[(n - 1) * NT1 + m];
-                I[n * NT1 + m + 1] = val;
+                double val = c0p * I[n][m];
+                if (m > 0) val += m * b01 * I[n][m - 1];
+                if (n > 0) val += n * b00 * I[n - 1][m];
+                I[n][m + 1] = val;
+            }
+        }
+        double* H = s.H[x][r];
+        B2_UNROLL
+        for (int l = 0; l <= C::LL; l++) {
+            double cf[C::LL + 1];
+            B2_UNROLL
+            for (int t = 0; t <= C::LL; t++) cf[t] = s.ccd[x][l][t];
+            B2_UNROLL
+            for (int k = 0; k <= C::LK; k++) {
+                B2_UNROLL
+                for (int n = 0; n <= C::LB; n++) {
+                    double acc = 0.0;
+                    B2_UNROLL
+                    for (int t = 0; t <= l; t++) acc += cf[t] * I[n][k + t];
+                    H[(l * (C::LK + 1) + k) * C::NB1P + n] = acc;
+                }
             }
         }
     }
 }
 
-// thread-local horizontal recurrences for one direction: out[j*(LI+1)+i]
+// thread-local bra transfer (i -> j) for one direction from the row H(.; k,l): out[j*(LI+1)+i]
 template <class C>
-B2_HD void hrr_dir(const double* I, int k, int l, const double (*ccd)[C::LL + 1], double AB, double* out)
+B2_HD void hrr_dir(const double* H, int k, int l, double AB, double* out)
 {
-    double T[C::NB1];
+    double T[C::NB1P];
+    const double* row = H + (l * (C::LK + 1) + k) * C::NB1P;
+#if defined(__CUDA_ARCH__)
     B2_UNROLL
-    for (int n = 0; n <= C::LB; n++) {
-        double sacc = 0.0;
-        B2_UNROLL
-        for (int t = 0; t <= C::LL; t++) sacc += ccd[l][t] * I[n * C::NT1 + k + t];
-        T[n] = sacc;
+    for (int n = 0; n < C::NB1P; n += 2) {
+        double2 v2 = *reinterpret_cast<const double2*>(row + n);   // 16-byte aligned by construction
+        T[n] = v2.x; T[n + 1] = v2.y;
     }
+#else
+    for (int n = 0; n < C::NB1; n++) T[n] = row[n];
+#endif
     B2_UNROLL
     for (int i = 0; i <= C::LI; i++) out[i] = T[i];
     B2_UNROLL
@@ -325,9 +346,9 @@ B2_HD void phase_accumulate(const SlotSmem<C>& s, ThreadCtx<C>& t, double ABx, d
 {
     for (int r = 0; r < C::NR; r++) {
         double gx[C::NI1 * C::NJ1], gy[C::NI1 * C::NJ1], gz[C::NI1 * C::NJ1];
-        hrr_dir<C>(s.I[0][r], t.kx, t.lx, s.ccd[0], ABx, gx);
-        hrr_dir<C>(s.I[1][r], t.ky, t.ly, s.ccd[1], ABy, gy);
-        hrr_dir<C>(s.I[2][r], t.kz, t.lz, s.ccd[2], ABz, gz);
+        hrr_dir<C>(s.H[0][r], t.kx, t.lx, ABx, gx);
+        hrr_dir<C>(s.H[1][r], t.ky, t.ly, ABy, gy);
+        hrr_dir<C>(s.H[2][r], t.kz, t.lz, ABz, gz);
         PartDispatch<C, 0>::run(t.p, t.v, gx, gy, gz);
     }
 }
