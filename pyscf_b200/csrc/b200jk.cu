@@ -227,7 +227,6 @@ extern "C" int b200jk_set_screening(b200jk_handle h, double tol, double omega)
             // AO block, consecutive primitive ranges).  Integrals are linear in the primitive sum and the unique-quartet
             // rule works on list positions, so (a+b|a+b)/2 = (a|a)/2 + (b|a) + (b|b)/2 is reproduced exactly; it bounds
             // the serial primitive loop of one thread/group (4096 -> 256 for the C 1s x C 1s pairs).
-            constexpr int MAX_PRIM_PER_PAIR = 16;
             for (auto& sp : P.all) {
                 if (!(sp.q * qmax > tol * 1e-2)) continue;
                 for (int p0 = 0; p0 < sp.nprim; p0 += MAX_PRIM_PER_PAIR) {

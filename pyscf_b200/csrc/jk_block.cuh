@@ -42,7 +42,8 @@ struct GroupCfg {
     static constexpr int TG = GW * 32;                                       // threads per group
     static constexpr int QPG = GP <= 32 ? 32 / GP : 1;                       // quartets in flight per group
     static constexpr int NG0 = 192 / TG;
-    static constexpr int NG = NG0 < 1 ? 1 : (NG0 > 8 ? 8 : NG0);             // groups per CTA
+    static constexpr int NG1 = NG0 < 1 ? 1 : (NG0 > 8 ? 8 : NG0);
+    static constexpr int NG = (NG1 * QPG > 64) ? ((64 / QPG) < 1 ? 1 : 64 / QPG) : NG1;   // groups per CTA, <= 64 quartet slots
     static constexpr int NT = NG * TG;
     static constexpr int NSLOT = NG * QPG;
 };
@@ -51,6 +52,9 @@ template <class C>
 struct BlockSmem {
     SlotSmem<C> slot[GroupCfg<C>::NSLOT];
     BraInfo bra;
+    PrimPair bprim[MAX_PRIM_PER_PAIR];                 // the stationary bra pair's primitive pairs (bulk async copy)
+    unsigned long long mbar_bra;                        // mbarriers of the bulk copies
+    unsigned long long mbar_slot[GroupCfg<C>::NSLOT];
     int klist[KCH_MAX];
     int nk;
     int next;
@@ -63,6 +67,7 @@ struct LaneCtx {
     double jij[C::NV];
     int grp, lt, slot, valid;
     int ibp, ikp;
+    unsigned kpar;   // phase parity of this slot's copy barrier
 };
 
 #if defined(__CUDA_ARCH__)
@@ -85,6 +90,26 @@ __device__ __forceinline__ void group_sync(int grp)
 #define B2_CTX(tid) ctxs[tid]
 template <class C>
 inline void group_sync(int) {}
+#endif
+
+#if defined(__CUDA_ARCH__)
+// 1-D bulk asynchronous copy global -> shared (TMA engine, SASS UBLKCP) completing on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void bulk_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned b = (unsigned)__cvta_generic_to_shared(bar), ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+    } while (!ok);
+}
 #endif
 
 // One group's life: pull ket batches until the CTA's list is exhausted.
@@ -138,6 +163,11 @@ void group_proc(const KParams& P, BlockSmem<C>& sm, int grp, int nk, int bx,
                         if (P.same_class && kk == bx) f *= 0.5;
                         s.fac = f;
                         slot_set_cd<C>(s, kp.ABx, kp.ABy, kp.ABz);
+#if defined(__CUDA_ARCH__)
+                        bulk_g2s(s.kprim, P.prims + kp.prim_off, (unsigned)kp.nprim * (unsigned)sizeof(PrimPair), &sm.mbar_slot[L.slot]);
+#else
+                        for (int e2 = 0; e2 < kp.nprim; e2++) s.kprim[e2] = P.prims[kp.prim_off + e2];
+#endif
                     } else {
                         s.nprim_k = 0;
                     }
@@ -148,6 +178,9 @@ void group_proc(const KParams& P, BlockSmem<C>& sm, int grp, int nk, int bx,
             }
         B2_END
         group_sync<C>(grp);
+#if defined(__CUDA_ARCH__)
+        if (ctx.valid && sm.slot[ctx.slot].active) { bulk_wait(&sm.mbar_slot[ctx.slot], ctx.kpar); ctx.kpar ^= 1; }
+#endif
         int npmax = 0;
         for (int q = 0; q < GC::QPG; q++) {
             int nk_ = sm.slot[grp * GC::QPG + q].nprim_k;
@@ -162,7 +195,7 @@ void group_proc(const KParams& P, BlockSmem<C>& sm, int grp, int nk, int bx,
                 if (L.valid) {
                     SlotSmem<C>& s = sm.slot[L.slot];
                     if (s.active && L.ibp < nbp)
-                        phase_roots<C>(s, L.t.g, P.prims[sm.bra.prim_off + L.ibp], P.prims[s.prim_off_k + L.ikp], P.tb, P.omega);
+                        phase_roots<C>(s, L.t.g, sm.bprim[L.ibp], s.kprim[L.ikp], P.tb, P.omega);
                 }
             B2_END
             group_sync<C>(grp);
@@ -240,9 +273,27 @@ void jk_block(const KParams& P, int bx, int by, BlockSmem<C>& sm)
             sm.bra.nprim = bpair.nprim; sm.bra.prim_off = bpair.prim_off;
             sm.bra.same = bpair.same; sm.bra.idx = bx;
             sm.nk = 0; sm.next = 0;
+#if defined(__CUDA_ARCH__)
+            for (int i = 0; i < GC::NSLOT; i++) {
+                unsigned a = (unsigned)__cvta_generic_to_shared(&sm.mbar_slot[i]);
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a));
+            }
+            {
+                unsigned a = (unsigned)__cvta_generic_to_shared(&sm.mbar_bra);
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a));
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            bulk_g2s(sm.bprim, P.prims + bpair.prim_off, (unsigned)bpair.nprim * (unsigned)sizeof(PrimPair), &sm.mbar_bra);
+#else
+            for (int e2 = 0; e2 < bpair.nprim; e2++) sm.bprim[e2] = P.prims[bpair.prim_off + e2];
+#endif
         }
+        L.kpar = 0;
     B2_END
     B2_SYNC();
+#if defined(__CUDA_ARCH__)
+    bulk_wait(&sm.mbar_bra, 0);
+#endif
 
     // ---- on-device screening: compact the surviving kets of this chunk
     B2_ALL_THREADS(tid)

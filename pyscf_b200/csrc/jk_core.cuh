@@ -120,6 +120,8 @@ struct ShellPair {  // 48 bytes
     int32_t pad;
 };
 
+constexpr int MAX_PRIM_PER_PAIR = 16;   // pair lists are split so that no entry carries more primitive pairs (b200jk.cu)
+
 // ---------------------------------------------------------------------------------------------
 template <int LI_, int LJ_, int LK_, int LL_, int NP_>
 struct QClass {
@@ -144,6 +146,7 @@ struct alignas(16) SlotSmem {
     // 2-D integrals after the vertical recurrence AND the ket transfer (k -> l), ready for per-thread bra transfer:
     // H[dir][root][(l*(LK+1)+k)*NB1P + n]; z carries weight*prefactor.  Rows of n are contiguous (LDS.128).
     double H[3][C::NR][C::HSP];
+    PrimPair kprim[MAX_PRIM_PER_PAIR];   // this ket's primitive pairs, staged by one bulk async copy (TMA, UBLKCP) per batch
     double U[C::NR], W[C::NR];
     double pc[14];               // p, q, PA[3], QC[3], PQ[3], 1/(p+q), 0.5/p, 0.5/q
     double ccd[3][C::LL + 1][C::LL + 1];  // binom(l,t) CD^(l-t)
