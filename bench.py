@@ -127,7 +127,7 @@ def run_ours(args, rank, world):
     occ_h = np.ascontiguousarray(c_occ * np.sqrt(2.0))
     t0 = time.time()
     if is_df:
-        eng = DF(mol, device=local).build()
+        eng = DF(mol, device=local, shard=(rank, world) if world > 1 else None).build()
         h = eng._handle
     else:
         eng = VHFOpt(mol, direct_scf_tol=1e-13, device=local)

@@ -77,7 +77,11 @@ int b200jk_df_jk_device(b200jk_handle h, const double* dm_dev, int n_dm, int nao
 /* K-build engine for the occupied-orbital path: mode 1 (default) = tcgen05 int8-slice GEMMs (i8gemm.cuh) with
  * `nslices` 7-bit slices (7 -> ~1e-11 relative), mode 0 = cuBLAS DGEMM on the FP64 pipe (kept as yardstick). */
 int b200jk_df_set_kmode(b200jk_handle h, int mode, int nslices);
-/* Rows [r0, r0+nr) of the device-resident tensor, reference layout cderi[naux, nao(nao+1)/2]
+/* Rows of the tensor held by this handle: [row0, row0+nrow) of the naux rows.  The whole tensor unless
+ * b200jk_set_shard(rank, world) was called BEFORE b200jk_df_build, in which case only this rank's rows are built
+ * (the 3-center integrals are computed in bounded batches of AO shell pairs and multiplied by this rank's rows of L^-1). */
+int b200jk_df_local_rows(b200jk_handle h, int* row0, int* nrow);
+/* Rows [r0, r0+nr) (LOCAL indices) of the device-resident tensor, reference layout cderi[naux, nao(nao+1)/2]
  * (pyscf/df/incore.py:134-136; what DF.loop() yields, pyscf/df/df.py:214-242). */
 int b200jk_df_get_cderi(b200jk_handle h, double* out, int r0, int nr);
 

@@ -48,6 +48,8 @@ struct DFState {
     int64_t rowlen = 0;
     int64_t* d_pairoff = nullptr;
     long npair = 0;
+    std::vector<int64_t> ao_off_h[NPC];
+    int build_rank = 0, build_world = 1, row0 = 0, nrow = 0;   // rows [row0, row0+nrow) of the tensor live on this rank
     double* d_cderi = nullptr;
     double omega = 0.0;
     // J/K workspaces
@@ -178,6 +180,11 @@ struct UnpackFn {
     }
 };
 
+struct IdentityFn { double* a; int n; B2_HD void operator()(long i) const { a[i * (long)n + i] = 1.0; } };
+struct GatherRowsFn {   // out[i][j] = X_colmajor[(r0+i), j]
+    const double* x; double* out; int n, r0;
+    B2_HD void operator()(long idx) const { long i = idx / n, j = idx - i * n; out[idx] = x[(r0 + i) + j * (long)n]; }
+};
 struct TransposeFn {   // out[c][r] = in[r][c]
     const double* in; double* out; int rows, cols;
     B2_HD void operator()(long idx) const { long r = idx / cols, c = idx - r * cols; out[c * (long)rows + r] = in[idx]; }
@@ -361,6 +368,7 @@ extern "C" int b200jk_df_build(b200jk_handle h, const int32_t* aux_atm, int aux_
                 off += (int64_t)ncart(h->pc[c].la) * ncart(h->pc[c].lb);
             }
             d->d_ao_off[c] = upload(o);
+            d->ao_off_h[c] = o;
         }
         d->rowlen = off;
         d->d_pairoff = upload(pairoff);
@@ -447,69 +455,98 @@ extern "C" int b200jk_df_build(b200jk_handle h, const int32_t* aux_atm, int aux_
 #endif
         d->naux = nkeep;
 
-        // ---- (ij|P): Cartesian rows -> spherical aux -> packed spherical pairs -> L^-1
-        const long npair = d->npair;
-        size_t cart_bytes = (size_t)nac * d->rowlen * 8, sphaux_bytes = (size_t)nas * d->rowlen * 8;
-        double* d_xc = (double*)dev_alloc(cart_bytes);
-        dev_zero(d_xc, cart_bytes, st);
-        for (int cb = 0; cb < NPC; cb++) {
-            if (h->pc[cb].all.empty()) continue;
-            for (int lk = 0; lk <= LMAX; lk++) {
-                if (d->akets[lk].empty()) continue;
-                J3cParams P{};
-                P.bra_pairs = h->pc[cb].d_all; P.nbra = (int)h->pc[cb].all.size(); P.bra_out_off = d->d_ao_off[cb];
-                P.ket_shells = d->d_akets[lk]; P.nket = (int)d->akets[lk].size();
-                P.bra_prims = h->d_prims; P.ket_prims = d->d_aprims;
-                P.tb = h->tb; P.omega = omega; P.out = d_xc; P.row_stride = d->rowlen;
-                launch_j3c(cb, lk, P, st);
-            }
-        }
-        double* d_xa = (double*)dev_alloc(sphaux_bytes);
-        AuxC2SFn a2 {d_xc, d_xa, d->rowlen, nas, d->d_asph_sh, d->d_asph_m, d->d_ash_l, d->d_ash_cart, h->d_c2s_off, h->d_c2s};
-        launch_1d((long)nas * d->rowlen, a2, st);
+        // ---- rows of the metric transform owned by this rank: T[nloc][nas] (rows of L^-1, or of W = diag(w)^-1/2 V^T)
+        const int bw = h->shard_world, br = h->shard_rank;
+        const int r_lo = (int)((long)nkeep * br / bw), r_hi = (int)((long)nkeep * (br + 1) / bw);
+        const int nloc = r_hi - r_lo;
+        d->build_rank = br; d->build_world = bw; d->row0 = r_lo; d->nrow = nloc;
+        double* d_T = (double*)dev_alloc((size_t)std::max(nloc, 1) * nas * 8);
 #ifndef B200JK_EMULATE
-        CK(cudaStreamSynchronize(st));
-#endif
-        dev_free(d_xc);
-        double* d_j3c = (double*)dev_alloc((size_t)nas * npair * 8);
-        PairC2SFn p2 {d_xa, d_j3c, d->rowlen, npair, nsh, d->d_pairoff, h->d_sph_sh, h->d_sph_m, h->d_sh_l, h->d_c2s_off, h->d_c2s};
-        launch_1d((long)nas * npair, p2, st);
-#ifndef B200JK_EMULATE
-        CK(cudaStreamSynchronize(st));
-        dev_free(d_xa);
         if (use_chol) {
-            // row-major j3c[naux, npair] == column-major [npair, naux]:  X * L^T = B  (right side, lower, transposed)
+            // L^-1 by one triangular solve against the identity (naux^2, setup only), then gather this rank's rows
+            double* d_inv = (double*)dev_alloc((size_t)nas * nas * 8);
+            dev_zero(d_inv, (size_t)nas * nas * 8, st);
+            IdentityFn idf{d_inv, nas};
+            launch_1d(nas, idf, st);
             const double one = 1.0;
-            CKB(cublasDtrsm(d->cublas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)npair, nas,
-                            &one, d_j2c, nas, d_j3c, (int)npair));
-            d->d_cderi = d_j3c;
-        } else {
-            // cderi = W j3c ; column-major: C[npair, nkeep] = B[npair, nas] * W^T[nas, nkeep]
-            double* d_W = upload(W);
-            d->d_cderi = (double*)dev_alloc((size_t)nkeep * npair * 8);
-            const double one = 1.0, zero = 0.0;
-            CKB(cublasDgemm(d->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)npair, nkeep, nas, &one, d_j3c, (int)npair, d_W, nas, &zero,
-                            d->d_cderi, (int)npair));
+            CKB(cublasDtrsm(d->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, nas, nas, &one, d_j2c, nas,
+                            d_inv, nas));
+            GatherRowsFn gf{d_inv, d_T, nas, r_lo};   // d_inv is column-major: X[(i) + j*n]
+            launch_1d((long)nloc * nas, gf, st);
             CK(cudaStreamSynchronize(st));
-            dev_free(d_W); dev_free(d_j3c);
+            dev_free(d_inv);
+        } else {
+            h2d(d_T, W.data() + (size_t)r_lo * nas, (size_t)nloc * nas * 8, st);
         }
-        CK(cudaStreamSynchronize(st));
 #else
-        dev_free(d_xa);
-        {   // forward substitution row by row on the host (tests only)
-            double* X = d_j3c;
-            for (int i = 0; i < nas; i++) {
-                for (int k = 0; k < i; k++) {
-                    double lik = j2c_h[(size_t)i * nas + k];
-                    if (lik == 0.0) continue;
-                    for (long t = 0; t < npair; t++) X[(size_t)i * npair + t] -= lik * X[(size_t)k * npair + t];
+        {   // host: rows of L^-1 by forward substitution on unit vectors (tests only)
+            std::vector<double> inv((size_t)nas * nas, 0.0);
+            for (int c = 0; c < nas; c++) {
+                for (int i = c; i < nas; i++) {
+                    double sacc = (i == c) ? 1.0 : 0.0;
+                    for (int k = c; k < i; k++) sacc -= j2c_h[(size_t)i * nas + k] * inv[(size_t)k * nas + c];
+                    inv[(size_t)i * nas + c] = sacc / j2c_h[(size_t)i * nas + i];
                 }
-                double inv = 1.0 / j2c_h[(size_t)i * nas + i];
-                for (long t = 0; t < npair; t++) X[(size_t)i * npair + t] *= inv;
             }
-            d->d_cderi = d_j3c;
+            memcpy(d_T, inv.data() + (size_t)r_lo * nas, (size_t)nloc * nas * 8);
         }
 #endif
+
+        // ---- (ij|P) in batches of AO shell pairs (bounded scratch): Cartesian rows -> spherical aux -> T . (P|ij)
+        const long npair = d->npair;
+        double* d_ycart = (double*)dev_alloc((size_t)std::max(nloc, 1) * d->rowlen * 8);
+        const int64_t budget_cols = std::max<int64_t>(4096, (int64_t)((3ULL << 30) / ((size_t)nac * 8)));
+        double* d_xc = (double*)dev_alloc((size_t)nac * (size_t)std::min<int64_t>(budget_cols + 128, d->rowlen) * 8);
+        double* d_xa = (double*)dev_alloc((size_t)nas * (size_t)std::min<int64_t>(budget_cols + 128, d->rowlen) * 8);
+        for (int cb = 0; cb < NPC; cb++) {
+            const auto& offs = d->ao_off_h[cb];
+            const int np_all = (int)h->pc[cb].all.size();
+            if (np_all == 0) continue;
+            const int64_t blk = (int64_t)ncart(h->pc[cb].la) * ncart(h->pc[cb].lb);
+            int p0 = 0;
+            while (p0 < np_all) {
+                int p1 = (int)std::min<int64_t>(np_all, p0 + std::max<int64_t>(1, budget_cols / blk));
+                const int64_t col0 = offs[p0], cols = (int64_t)(p1 - p0) * blk;
+                for (int lk = 0; lk <= LMAX; lk++) {
+                    if (d->akets[lk].empty()) continue;
+                    J3cParams P{};
+                    P.bra_pairs = h->pc[cb].d_all + p0; P.nbra = p1 - p0; P.bra_out_off = d->d_ao_off[cb] + p0;
+                    P.ket_shells = d->d_akets[lk]; P.nket = (int)d->akets[lk].size();
+                    P.bra_prims = h->d_prims; P.ket_prims = d->d_aprims;
+                    P.tb = h->tb; P.omega = omega; P.out = d_xc; P.row_stride = cols; P.col0 = col0;
+                    launch_j3c(cb, lk, P, st);
+                }
+                AuxC2SFn a2 {d_xc, d_xa, cols, nas, d->d_asph_sh, d->d_asph_m, d->d_ash_l, d->d_ash_cart, h->d_c2s_off, h->d_c2s};
+                launch_1d((long)nas * cols, a2, st);
+                if (nloc > 0) {
+#ifndef B200JK_EMULATE
+                    // row-major Y[nloc, cols] (ld rowlen) = T[nloc, nas] . Xa[nas, cols]  <=>  col-major Y^T = Xa^T . T^T
+                    const double one = 1.0, zero = 0.0;
+                    CKB(cublasDgemm(d->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)cols, nloc, nas, &one, d_xa, (int)cols, d_T, nas, &zero,
+                                    d_ycart + col0, (int)d->rowlen));
+#else
+                    for (int i = 0; i < nloc; i++)
+                        for (int64_t c = 0; c < cols; c++) {
+                            double acc = 0.0;
+                            for (int k = 0; k < nas; k++) acc += d_T[(size_t)i * nas + k] * d_xa[(size_t)k * cols + c];
+                            d_ycart[(size_t)i * d->rowlen + col0 + c] = acc;
+                        }
+#endif
+                }
+                p0 = p1;
+            }
+        }
+#ifndef B200JK_EMULATE
+        CK(cudaStreamSynchronize(st));
+#endif
+        dev_free(d_xc); dev_free(d_xa); dev_free(d_T);
+        d->d_cderi = (double*)dev_alloc((size_t)std::max(nloc, 1) * npair * 8);
+        PairC2SFn p2 {d_ycart, d->d_cderi, d->rowlen, npair, nsh, d->d_pairoff, h->d_sph_sh, h->d_sph_m, h->d_sh_l, h->d_c2s_off, h->d_c2s};
+        launch_1d((long)nloc * npair, p2, st);
+#ifndef B200JK_EMULATE
+        CK(cudaStreamSynchronize(st));
+#endif
+        dev_free(d_ycart);
         dev_free(d_j2c_cart); dev_free(d_j2c);
     } catch (std::exception& e) { set_err(h, e.what()); return 2; }
     return 0;
@@ -522,13 +559,20 @@ extern "C" int b200jk_df_naux(b200jk_handle h, int* naux)
     return 0;
 }
 
+extern "C" int b200jk_df_local_rows(b200jk_handle h, int* row0, int* nrow)
+{
+    if (!h || !h->df || !row0 || !nrow) { set_err(h, "call b200jk_df_build first"); return 1; }
+    *row0 = h->df->row0; *nrow = h->df->nrow;
+    return 0;
+}
+
 // cderi rows [r0, r0+nr) copied to the host (tests, interchange with PySCF's with_df._cderi)
 extern "C" int b200jk_df_get_cderi(b200jk_handle h, double* out, int r0, int nr)
 {
     if (!h || !h->df || !h->df->d_cderi) { set_err(h, "call b200jk_df_build first"); return 1; }
     try {
         DFState* d = h->df;
-        if (r0 < 0 || nr < 0 || r0 + nr > d->naux) throw std::runtime_error("row range out of bounds");
+        if (r0 < 0 || nr < 0 || r0 + nr > d->nrow) throw std::runtime_error("row range out of bounds (rows are local to this rank)");
         d2h(out, d->d_cderi + (size_t)r0 * d->npair, (size_t)nr * d->npair * 8);
         dev_sync();
     } catch (std::exception& e) { set_err(h, e.what()); return 2; }
@@ -547,9 +591,12 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
         (void)hermi;
         auto t0 = std::chrono::steady_clock::now();
         const long npair = d->npair, n2 = (long)nao * nao;
-        const int naux = d->naux;
+        const int naux = std::max(d->nrow, 1);   // rows held locally
         // multi-GPU: this rank contracts only its auxiliary rows [r_lo, r_hi) and returns partial J/K
-        const int r_lo = (int)((long)naux * h->shard_rank / h->shard_world), r_hi = (int)((long)naux * (h->shard_rank + 1) / h->shard_world);
+        int r_lo, r_hi;   // LOCAL row indices into d_cderi
+        if (d->build_world == h->shard_world && d->build_rank == h->shard_rank) { r_lo = 0; r_hi = d->nrow; }
+        else if (d->build_world == 1) { r_lo = (int)((long)d->nrow * h->shard_rank / h->shard_world); r_hi = (int)((long)d->nrow * (h->shard_rank + 1) / h->shard_world); }
+        else throw std::runtime_error("the tensor was built for a different shard; call b200jk_df_build again after b200jk_set_shard");
 #ifndef B200JK_EMULATE
         CK(cudaSetDevice(h->device));
         cudaStream_t st = h->stream;

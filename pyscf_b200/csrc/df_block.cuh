@@ -21,6 +21,7 @@ struct J3cParams {
     RysTables tb;
     double omega;
     double* out; int64_t row_stride;          // out row = auxiliary Cartesian function (ket i0 + c)
+    int64_t col0;                              // column offset of this batch of bra pairs inside the full row
     int kchunk;
 };
 
@@ -38,7 +39,7 @@ void j3c_block(const J3cParams& P, int bx, int by, BlockSmem<C>& sm)
     const int kbeg = by * P.kchunk;
     const int kend = (kbeg + P.kchunk < P.nket) ? kbeg + P.kchunk : P.nket;
     if (kbeg >= kend) return;
-    const int64_t boff = P.bra_out_off[bx];
+    const int64_t boff = P.bra_out_off[bx] - P.col0;
 #if defined(__CUDA_ARCH__)
     LaneCtx<C> ctx;
 #else

@@ -18,12 +18,13 @@ from .gto.mole import make_auxmol
 
 
 class DF:
-    def __init__(self, mol, auxbasis=None, device=0, libpath=None):
+    def __init__(self, mol, auxbasis=None, device=0, libpath=None, shard=None):
         self.mol = mol
         self.auxbasis = auxbasis
         self.auxmol = None
         self.device = device
         self._libpath = libpath
+        self.shard = shard         # (rank, world): build only this rank's auxiliary rows (multi-GPU, see parallel.py)
         self._handle = None
         self._rsh_df = {}          # omega -> DF (pyscf/df/df.py:298-333 range_coulomb)
         self.omega = None
@@ -47,6 +48,8 @@ class DF:
         bas = np.ascontiguousarray(aux._bas, dtype=np.int32)
         env = np.ascontiguousarray(aux._env, dtype=np.float64)
         omega = 0.0 if self.omega is None else float(self.omega)
+        if self.shard is not None:
+            h.check(h.lib.b200jk_set_shard(h._h, int(self.shard[0]), int(self.shard[1])), 'b200jk_set_shard')
         h.check(h.lib.b200jk_df_build(h._h, _lib.iptr(atm), len(atm), _lib.iptr(bas), len(bas), _lib.dptr(env), len(env),
                                       omega, self.lindep), 'b200jk_df_build')
         self._handle = h
@@ -82,7 +85,11 @@ class DF:
 
     def loop(self, blksize=None):
         """Yield host copies of cderi row blocks [nrow, nao(nao+1)/2] (pyscf/df/df.py:214-242)."""
-        naux = self.get_naoaux()
+        self.get_naoaux()
+        row0, naux = ctypes.c_int(0), ctypes.c_int(0)
+        self._handle.check(self._handle.lib.b200jk_df_local_rows(self._handle._h, ctypes.byref(row0), ctypes.byref(naux)),
+                           'b200jk_df_local_rows')
+        naux = naux.value      # rows held by this rank (all of them unless the build was sharded)
         blksize = blksize or self.blockdim
         npair = self.nao * (self.nao + 1) // 2
         h = self._handle

@@ -29,7 +29,7 @@ _libs = {}
 SYMBOLS = ['b200jk_create', 'b200jk_destroy', 'b200jk_set_screening', 'b200jk_direct_jk', 'b200jk_direct_jk_device',
            'b200jk_df_build', 'b200jk_df_jk', 'b200jk_df_naux', 'b200jk_get_q_cond', 'b200jk_get_stats',
            'b200jk_last_error', 'b200jk_version', 'b200jk_set_stream', 'b200jk_fp64_peak',
-           'b200jk_set_profile', 'b200jk_get_class_times', 'b200jk_df_get_cderi', 'b200jk_i8gemm_test', 'b200jk_df_set_kmode', 'b200jk_set_shard', 'b200jk_df_jk_device']
+           'b200jk_set_profile', 'b200jk_get_class_times', 'b200jk_df_get_cderi', 'b200jk_i8gemm_test', 'b200jk_df_set_kmode', 'b200jk_set_shard', 'b200jk_df_jk_device', 'b200jk_df_local_rows']
 
 
 def load(path=None):
@@ -56,6 +56,7 @@ def load(path=None):
     lib.b200jk_i8gemm_test.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p,
                                        ctypes.c_int, ctypes.c_int]
     lib.b200jk_df_set_kmode.argtypes = [vp, ctypes.c_int, ctypes.c_int]
+    lib.b200jk_df_local_rows.argtypes = [vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
     lib.b200jk_set_shard.argtypes = [vp, ctypes.c_int, ctypes.c_int]
     lib.b200jk_df_jk_device.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp, vp]
     lib.b200jk_get_q_cond.argtypes = [vp, c_double_p, ctypes.c_int]

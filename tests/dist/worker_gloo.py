@@ -37,6 +37,13 @@ ref, _ = O.cholesky_eri(mol, make_auxmol(mol, 'weigend'))
 vj, vk = sd.get_jk(dm)
 rj, rk = O.df_get_jk(ref, nao, dm)
 assert abs(vj - rj).max() < 1e-10 and abs(vk - rk).max() < 1e-10
+# sharded BUILD: each rank builds only its rows of cderi
+dfs = DF(mol, 'weigend', libpath=emu, shard=(rank, dist.get_world_size())).build()
+assert dfs._cderi.shape[0] < ref.shape[0]
+vj, vk = ShardedJK(dfs).get_jk(dm)
+assert abs(vj - rj).max() < 1e-10 and abs(vk - rk).max() < 1e-10
+lo = ref.shape[0] * rank // dist.get_world_size()
+assert abs(dfs._cderi - ref[lo:lo + dfs._cderi.shape[0]]).max() < 1e-9
 dist.barrier()
 if rank == 0:
     print('GLOO_SHARD_OK')
