@@ -37,6 +37,8 @@ WORKLOADS = {
     'h2o-ccpvdz-direct': dict(geom='h2o', basis='cc-pvdz', nocc=5, kind='direct'),
     'c60-def2svp-df': dict(geom='c60', basis='def2-svp', nocc=180, kind='df'),
     'benzene-def2svp-df': dict(geom='benzene', basis='def2-svp', nocc=21, kind='df'),
+    'gly30-ccpvdz-df': dict(geom='gly30', basis='cc-pvdz', nocc=455, kind='df'),   # BASELINE config 5 (full-range J/K part)
+    'gly4-ccpvdz-df': dict(geom='gly4', basis='cc-pvdz', nocc=65, kind='df'),
 }
 
 def scf_like_dm(nao, nocc, seed=1):

@@ -26,6 +26,10 @@ def test_table_sizes_match_survey():
     assert (m.nbas, m.nao) == (360, 840)
     aux = make_auxmol(m)
     assert (aux.nbas, aux.nao, int(aux._bas[:, 1].max())) == (1500, 4500, 4)
+    m = gto.M(atom=geometry('gly30'), basis='cc-pvdz')       # config 5: C60H92N30O31
+    assert (m.natm, m.nbas, m.nao, m.nelectron // 2) == (213, 881, 2154, 455)
+    aux = make_auxmol(m)
+    assert (aux.nbas, aux.nao) == (3732, 10586)
 
 
 def test_env_layout():
