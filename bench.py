@@ -226,6 +226,7 @@ def run_ours(args, rank, world):
     if rank != 0:
         if world > 1:
             dist.barrier()
+            dist.destroy_process_group()
         return
     # ---- roofline
     peaks = {}
@@ -301,6 +302,7 @@ def run_ours(args, rank, world):
     print(json.dumps(out))
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
 
 
 def cpu_baseline_df(mol, dm, c_occ, workload):

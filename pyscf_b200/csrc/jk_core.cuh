@@ -30,8 +30,9 @@ inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 #endif
 
 constexpr int LMAX = 4;  // g shells (aux); orbital classes are generated up to f
-constexpr int RYS_NMAX = 9, RYS_DEG = 13, RYS_NINT = 40;
-constexpr double RYS_H = 2.5, RYS_XMAX = 100.0;
+constexpr int RYS_NMAX = 9, RYS_DEG = 7, RYS_NINT = 320;   // degree-7 Chebyshev pieces on 320 intervals of 0.3125
+constexpr double RYS_H = 0.3125, RYS_XMAX = 100.0;
+constexpr int RYS_ROW = 2 * (RYS_DEG + 1);                  // doubles per (interval, root): node and weight polynomials
 constexpr double PI_25_2 = 34.98683665524972497;  // 2*pi^(5/2)
 
 B2_HD constexpr int ncart(int l) { return (l + 1) * (l + 2) / 2; }
@@ -63,7 +64,7 @@ B2_HD constexpr int cart_pz(int l, int a) { return l - cart_px(l, a) - cart_py(l
 // Rys roots and weights from the tables made by tools/gen_rys_tables.py
 struct RysTables {
     const double* herm;  // for n: offset n(n-1): u_r*x (n values), w_r*sqrt(x) (n values)
-    const double* cheb;  // for n: offset NINT*28*n(n-1)/2: [NINT][n][2][14]
+    const double* cheb;  // for n: offset NINT*RYS_ROW*n(n-1)/2: [NINT][n][2][DEG+1]
 };
 
 B2_HD void rys_root(const RysTables& tb, int n, int r, double x, double& u, double& w)
@@ -78,28 +79,28 @@ B2_HD void rys_root(const RysTables& tb, int n, int r, double x, double& u, doub
     int iv = (int)(x * (1.0 / RYS_H));
     if (iv > RYS_NINT - 1) iv = RYS_NINT - 1;
     double t = (x - iv * RYS_H) * (2.0 / RYS_H) - 1.0;
-    const double* cp = tb.cheb + (size_t)RYS_NINT * 28 * (n * (n - 1) / 2) + (size_t)(iv * n + r) * 28;
-    double c[28];
+    const double* cp = tb.cheb + (size_t)RYS_NINT * RYS_ROW * (n * (n - 1) / 2) + (size_t)(iv * n + r) * RYS_ROW;
+    double c[RYS_ROW];
 #if defined(__CUDA_ARCH__)
-    // one table row = 224 B = 7 x 256-bit loads (LDG.E.256 on sm_100a); rows are 32-byte aligned (b200jk_create)
+    // one table row = 128 B = 4 x 256-bit loads (LDG.E.256 on sm_100a); rows are 32-byte aligned (b200jk_create)
     B2_UNROLL
-    for (int j = 0; j < 7; j++)
+    for (int j = 0; j < RYS_ROW / 4; j++)
         asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
                      : "=d"(c[4 * j]), "=d"(c[4 * j + 1]), "=d"(c[4 * j + 2]), "=d"(c[4 * j + 3])
                      : "l"(cp + 4 * j));
 #else
-    for (int j = 0; j < 28; j++) c[j] = cp[j];
+    for (int j = 0; j < RYS_ROW; j++) c[j] = cp[j];
 #endif
     double t2 = 2.0 * t, b1 = 0.0, b2 = 0.0, d1 = 0.0, d2 = 0.0;
     B2_UNROLL
     for (int j = RYS_DEG; j >= 1; j--) {
         double tb_ = t2 * b1 - b2 + c[j];
         b2 = b1; b1 = tb_;
-        double td_ = t2 * d1 - d2 + c[14 + j];
+        double td_ = t2 * d1 - d2 + c[RYS_DEG + 1 + j];
         d2 = d1; d1 = td_;
     }
     u = t * b1 - b2 + c[0];
-    w = t * d1 - d2 + c[14];
+    w = t * d1 - d2 + c[RYS_DEG + 1];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -110,6 +111,19 @@ struct PrimPair {  // 64 bytes, one per surviving primitive pair
     double PAx, PAy, PAz; // P - A   (A = centre of the first shell of the pair)
     double cc;            // sqrt(2 pi^(5/2)) * c_i c_j exp(-a_i a_j |AB|^2 / p) / p
 };
+// one PrimPair = 64 B = two 256-bit loads (a quarter of the L1 tag traffic of eight 64-bit loads)
+B2_HD PrimPair load_prim(const PrimPair* p)
+{
+#if defined(__CUDA_ARCH__)
+    PrimPair r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.p), "=d"(r.Px), "=d"(r.Py), "=d"(r.Pz) : "l"(p));
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.PAx), "=d"(r.PAy), "=d"(r.PAz), "=d"(r.cc) : "l"((const double*)p + 4));
+    return r;
+#else
+    return *p;
+#endif
+}
+
 struct ShellPair {  // 48 bytes
     double ABx, ABy, ABz;  // A - B
     double q;              // Schwarz bound sqrt(max |(ab|ab)|) over Cartesian components

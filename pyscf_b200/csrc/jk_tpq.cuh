@@ -83,9 +83,9 @@ B2_HD void tpq_eri(const KParams& P, const ShellPair& bp, const ShellPair& kp, i
     B2_UNROLL
     for (int e = 0; e < T::NOUT; e++) v[e] = 0.0;
     for (int ib = ib0; ib < ib1; ib++) {
-        const PrimPair b = P.prims[bp.prim_off + ib];
+        const PrimPair b = load_prim(P.prims + bp.prim_off + ib);
         for (int ik = 0; ik < kp.nprim; ik++) {
-            const PrimPair k = P.prims[kp.prim_off + ik];
+            const PrimPair k = load_prim(P.prims + kp.prim_off + ik);
             double p = b.p, q = k.p;
             double PQx = b.Px - k.Px, PQy = b.Py - k.Py, PQz = b.Pz - k.Pz;
             double pq = p + q;

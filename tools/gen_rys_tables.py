@@ -24,9 +24,9 @@ import mpmath as mp
 import numpy as np
 
 NMAX = 9
-DEG = 13
-H = 2.5
-NINT = 40
+DEG = 7
+H = 0.3125
+NINT = 320
 XMAX = H * NINT
 mp.mp.dps = 80
 
