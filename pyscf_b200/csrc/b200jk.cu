@@ -345,10 +345,11 @@ static int direct_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, 
         for (const Job& jb : jobs) {
             int cb = jb.cb, ck = jb.ck;
             PairClass &B = h->pc[cb], &K = h->pc[ck];
+            // (measured: the thread-per-quartet kernels are also faster on the split lists — balance beats the extra digestions)
             P.bra_pairs = B.d_kept; P.nbra = (int)B.kept.size();
             P.ket_pairs = K.d_kept; P.nket = (int)K.kept.size();
             P.same_class = (cb == ck);
-            P.bra_nprim_max = B.kept[0].nprim;  // kept lists are sorted by primitive count, largest first
+            P.bra_nprim_max = B.kept[0].nprim;  // lists are sorted by primitive count, largest first
             P.ket_nprim_max = K.kept[0].nprim;
 #ifndef B200JK_EMULATE
             cudaStream_t ss = h->profile ? st : h->side[jn % h->side.size()];

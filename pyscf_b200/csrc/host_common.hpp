@@ -88,7 +88,7 @@ struct DevShell {
 struct PairClass {
     int la = 0, lb = 0;
     std::vector<ShellPair> all;      // every pair, unsorted, q not set
-    std::vector<ShellPair> kept;     // screened + sorted by q descending
+    std::vector<ShellPair> kept;     // screened, deeply contracted pairs split into sub-pairs, sorted (block kernels)
     ShellPair* d_all = nullptr;
     ShellPair* d_kept = nullptr;
 };

@@ -124,6 +124,14 @@ void launch_one(KParams P, b2_stream_t st)
 #define B2_PAIR_CASES(X) \
     X(0, 0, 0) X(1, 1, 0) X(2, 1, 1) X(3, 2, 0) X(4, 2, 1) X(5, 2, 2) X(6, 3, 0) X(7, 3, 1) X(8, 3, 2) X(9, 3, 3)
 
+// host-side mirror of TpqCfg<C>::eligible for the class (la lb|lc ld) as launched
+inline bool tpq_class(int la, int lb, int lc, int ld)
+{
+    int nout = ncart(la) * ncart(lb) * ncart(lc) * ncart(ld);
+    int nr = (la + lb + lc + ld) / 2 + 1;
+    return nout <= 36 && nr <= 3 && choose_np(ncart(la), ncart(lb), ncart(lc) * ncart(ld)) == 1;
+}
+
 // Orientation of a class pair (hi id > lo id): by default the larger class is the register-resident bra.  For these
 // pairs the opposite choice packs the warps better (threads = fs/fp components instead of dp/dd: 30 of 32 lanes
 // instead of 18) and needs fewer reductions per integral, so they run with bra = lo class, ket = hi class.

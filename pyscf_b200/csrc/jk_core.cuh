@@ -124,7 +124,7 @@ B2_HD PrimPair load_prim(const PrimPair* p)
 #endif
 }
 
-struct ShellPair {  // 48 bytes
+struct ShellPair {  // 64 bytes
     double ABx, ABy, ABz;  // A - B
     double q;              // Schwarz bound sqrt(max |(ab|ab)|) over Cartesian components
     int32_t ish, jsh;      // device shell ids
@@ -133,6 +133,25 @@ struct ShellPair {  // 48 bytes
     int32_t same;          // ish == jsh
     int32_t pad;
 };
+
+static_assert(sizeof(ShellPair) == 64, "ShellPair is loaded as two 256-bit words");
+// one ShellPair = 64 B = two 256-bit loads
+B2_HD ShellPair load_pair(const ShellPair* p)
+{
+#if defined(__CUDA_ARCH__)
+    ShellPair r;
+    unsigned long long w0, w1, w2, w3;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.ABx), "=d"(r.ABy), "=d"(r.ABz), "=d"(r.q) : "l"(p));
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w0), "=l"(w1), "=l"(w2), "=l"(w3) : "l"((const char*)p + 32));
+    r.ish = (int32_t)(w0 & 0xffffffffu); r.jsh = (int32_t)(w0 >> 32);
+    r.i0 = (int32_t)(w1 & 0xffffffffu); r.j0 = (int32_t)(w1 >> 32);
+    r.prim_off = (int32_t)(w2 & 0xffffffffu); r.nprim = (int32_t)(w2 >> 32);
+    r.same = (int32_t)(w3 & 0xffffffffu); r.pad = 0;
+    return r;
+#else
+    return *p;
+#endif
+}
 
 constexpr int MAX_PRIM_PER_PAIR = 16;   // pair lists are split so that no entry carries more primitive pairs (b200jk.cu)
 

@@ -266,7 +266,7 @@ void tpq_block(const KParams& P, int bx, int by, int bz)
         for (int e = 0; e < T::NAB; e++) jij[e] = 0.0;
         int mine = 0, skipped = 0;
         for (int kk = kbeg + tid; kk < kend; kk += T::NT) {
-            const ShellPair kp = P.ket_pairs[kk];
+            const ShellPair kp = load_pair(P.ket_pairs + kk);
             if (!keep_quartet(bpair.q, kp.q, bpair.ish, bpair.jsh, kp.ish, kp.jsh, P.dmc, P.nsh, P.tol, P.vj != nullptr,
                               P.vk != nullptr)) {
                 if (bz == 0) skipped++;
