@@ -200,7 +200,6 @@ extern "C" int b200jk_set_screening(b200jk_handle h, double tol, double omega)
 {
     if (!h) return 1;
     try {
-        if (omega < 0.0) throw std::runtime_error("short-range (omega<0) operator is not implemented on the device path");
         h->tol = tol; h->omega = omega;
         double qmax = 0.0;
         for (int c = 0; c < NPC; c++) {

@@ -340,7 +340,6 @@ extern "C" int b200jk_df_build(b200jk_handle h, const int32_t* aux_atm, int aux_
     if (!h) return 1;
     try {
         (void)aux_natm; (void)aux_nenv;
-        if (omega < 0.0) throw std::runtime_error("short-range (omega<0) operator is not implemented on the device path");
         if (h->df) { df_free(h->df); h->df = nullptr; }
         DFState* d = new DFState();
         h->df = d; h->df_free = df_free;

@@ -25,7 +25,7 @@ struct J3cParams {
     int kchunk;
 };
 
-template <class C>
+template <class C, bool SR>
 #ifdef __CUDACC__
 __device__ __forceinline__
 #else
@@ -102,7 +102,7 @@ void j3c_block(const J3cParams& P, int bx, int by, BlockSmem<C>& sm)
                     }
                     B2_UNROLL
                     for (int e = 0; e < C::NV; e++) L.t.v[e] = 0.0;
-                    L.ibp = 0; L.ikp = 0;
+                    L.ibp = 0; L.ikp = 0; L.sr = 0;
                 }
             B2_END
             group_sync<C>(grp);
@@ -112,13 +112,16 @@ void j3c_block(const J3cParams& P, int bx, int by, BlockSmem<C>& sm)
                 npmax = nk_ > npmax ? nk_ : npmax;
             }
             npmax *= nbp;
+            constexpr bool sr_op = SR;   // omega < 0: erfc = Coulomb - erf, two root sets per primitive pair
+            if (sr_op) npmax *= 2;
             for (int ip = 0; ip < npmax; ip++) {
                 B2_GROUP_LANES(lt)
                     LaneCtx<C>& L = B2_CTX(tid0 + lt);
                     if (L.valid) {
                         SlotSmem<C>& s = sm.slot[L.slot];
                         if (s.active && L.ibp < nbp)
-                            phase_roots<C>(s, L.t.g, P.bra_prims[sm.bra.prim_off + L.ibp], P.ket_prims[s.prim_off_k + L.ikp], P.tb, P.omega);
+                            phase_roots<C>(s, L.t.g, P.bra_prims[sm.bra.prim_off + L.ibp], P.ket_prims[s.prim_off_k + L.ikp], P.tb,
+                                           sr_op ? (L.sr ? -P.omega : 0.0) : P.omega, (sr_op && L.sr) ? -1.0 : 1.0);
                     }
                 B2_END
                 group_sync<C>(grp);
@@ -136,7 +139,8 @@ void j3c_block(const J3cParams& P, int bx, int by, BlockSmem<C>& sm)
                         SlotSmem<C>& s = sm.slot[L.slot];
                         if (s.active && L.ibp < nbp) {
                             phase_accumulate<C>(s, L.t, sm.bra.ABx, sm.bra.ABy, sm.bra.ABz);
-                            if (++L.ikp == s.nprim_k) { L.ikp = 0; L.ibp++; }
+                            if (sr_op && !L.sr) L.sr = 1;
+                            else { L.sr = 0; if (++L.ikp == s.nprim_k) { L.ikp = 0; L.ibp++; } }
                         }
                     }
                 B2_END

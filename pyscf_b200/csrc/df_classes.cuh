@@ -16,12 +16,28 @@ struct J3cCfg {
 };
 
 #ifndef B200JK_EMULATE
-template <class C>
+template <class C, bool SR>
 __global__ void __launch_bounds__(GroupCfg<C>::NT) j3c_kernel(const J3cParams P)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     BlockSmem<C>& sm = *reinterpret_cast<BlockSmem<C>*>(smraw);
-    j3c_block<C>(P, blockIdx.x, blockIdx.y, sm);
+    j3c_block<C, SR>(P, blockIdx.x, blockIdx.y, sm);
+}
+#endif
+
+#ifndef B200JK_EMULATE
+template <class C, bool SR>
+void launch_j3c_kernel(const J3cParams& P, dim3 grid, int nt, size_t smem, b2_stream_t st)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(j3c_kernel<C, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(j3c): ") + cudaGetErrorString(e));
+        configured = true;
+    }
+    j3c_kernel<C, SR><<<grid, nt, smem, st>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw std::runtime_error(std::string("j3c_kernel launch: ") + cudaGetErrorString(e));
 }
 #endif
 
@@ -33,22 +49,18 @@ void launch_j3c_one(J3cParams P, b2_stream_t st)
     P.kchunk = pick_kchunk(P.nbra, P.nket, GC::NSLOT, 4096);
     int ny = (P.nket + P.kchunk - 1) / P.kchunk;
 #ifndef B200JK_EMULATE
-    static bool configured = false;
     size_t smem = sizeof(BlockSmem<C>);
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(j3c_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(j3c): ") + cudaGetErrorString(e));
-        configured = true;
-    }
     dim3 grid(P.nbra, ny);
-    j3c_kernel<C><<<grid, GC::NT, smem, st>>>(P);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) throw std::runtime_error(std::string("j3c_kernel launch: ") + cudaGetErrorString(e));
+    if (P.omega < 0.0) launch_j3c_kernel<C, true>(P, grid, GC::NT, smem, st);
+    else launch_j3c_kernel<C, false>(P, grid, GC::NT, smem, st);
 #else
     (void)st;
     BlockSmem<C>* sm = new BlockSmem<C>();
     for (int bx = 0; bx < P.nbra; bx++)
-        for (int by = 0; by < ny; by++) j3c_block<C>(P, bx, by, *sm);
+        for (int by = 0; by < ny; by++) {
+            if (P.omega < 0.0) j3c_block<C, true>(P, bx, by, *sm);
+            else j3c_block<C, false>(P, bx, by, *sm);
+        }
     delete sm;
 #endif
 }

@@ -88,6 +88,8 @@ void gemm_ar(const SliceStack& A, int a_row0, int M, const SliceStack& B, double
     GemmParams P{};
     P.M = M; P.N = B.R; P.Kp = A.Kp; P.Mp = A.Rp; P.Np = B.Rp; P.ns = A.ns; P.symmetric = 0;
     P.Ea = A.E; P.Eb = B.E; P.C = C; P.ldc = ldc; P.inner = inner; P.a_row0 = a_row0; P.ksplit = 1; P.dbg = nullptr;
+    static const int stack = getenv("B200JK_AR_STACK") ? atoi(getenv("B200JK_AR_STACK")) : 1;   // 0: one slice pair per MMA (tuning yardstick)
+    P.stack = stack;
     dim3 grid((B.R + AR_BN - 1) / AR_BN, (M + BM - 1) / BM);
     i8gemm_ar_kernel<<<grid, NTHREADS, AR_SMEM_BYTES, st>>>(ta, tb, P);
     CK(cudaGetLastError());

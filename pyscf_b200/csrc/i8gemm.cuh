@@ -45,6 +45,7 @@ struct GemmParams {
     int a_row0;            // first row of the A stack used by this GEMM (row blocks of a persistent stack)
     int ksplit;            // K blocks are divided among gridDim.z CTAs (fp64 reductions make this safe)
     long long* dbg;        // optional cycle stamps of CTA (0,0) (tests/tuning)
+    int stack;             // i8gemm_ar_kernel: multiply A_k with up to 4 stacked B slices per MMA (N = 256)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -357,7 +358,6 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_i8(BM, AR_BN);
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
             for (int kb = 0; kb < nkb; kb++) {
                 mbar_wait(&bfull[sb], pb);
@@ -367,13 +367,20 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
                     mbar_wait(&afull[sa], pa);
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(sA + sa * AR_A_BYTES);
-                    for (int l = 0; l < ns - k; l++) {
+                    // The B slices l = 0..ns-1-k of this K block lie back to back in shared memory (64 rows x 128 B each),
+                    // i.e. they ARE one K-major tile of (ns-k)*64 rows, and their groups k+l are adjacent TMEM column
+                    // blocks: one MMA with N = 64*cnt multiplies A_k with cnt slices at once.  A 128-row MMA costs the
+                    // same ~128 cycles for any N <= 256, so stacking cuts the 28 slice-pair MMAs per K block to 10.
+                    const int lstep = P.stack ? 4 : 1;
+                    for (int l = 0; l < ns - k; l += lstep) {
+                        const int cnt = (ns - k - l < lstep) ? ns - k - l : lstep;
+                        const uint32_t idesc_n = make_idesc_i8(BM, cnt * AR_BN);
                         const uint32_t b0 = bbase + l * AR_B1_BYTES;
                         const uint32_t tacc = tmem_base + (k + l) * AR_BN;
                         uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;   // first touch of group k+l is (kb=0, k=0)
 #pragma unroll
                         for (int kk = 0; kk < BK / UK; kk++) {
-                            mma_i8(tacc, make_desc_k_sw128(a0 + kk * UK), make_desc_k_sw128(b0 + kk * UK), idesc, acc);
+                            mma_i8(tacc, make_desc_k_sw128(a0 + kk * UK), make_desc_k_sw128(b0 + kk * UK), idesc_n, acc);
                             acc = 1;
                         }
                     }

@@ -67,6 +67,7 @@ struct LaneCtx {
     double jij[C::NV];
     int grp, lt, slot, valid;
     int ibp, ikp;
+    int sr;          // omega < 0 only: 0 = Coulomb pass, 1 = (negated) erf pass of the current primitive quartet
     unsigned kpar;   // phase parity of this slot's copy barrier
 };
 
@@ -113,7 +114,7 @@ __device__ __forceinline__ void bulk_wait(unsigned long long* bar, unsigned pari
 #endif
 
 // One group's life: pull ket batches until the CTA's list is exhausted.
-template <class C>
+template <class C, bool SR>
 #ifdef __CUDACC__
 __device__ __forceinline__
 #else
@@ -174,7 +175,7 @@ void group_proc(const KParams& P, BlockSmem<C>& sm, int grp, int nk, int bx,
                 }
                 B2_UNROLL
                 for (int e = 0; e < C::NV; e++) L.t.v[e] = 0.0;
-                L.ibp = 0; L.ikp = 0;
+                L.ibp = 0; L.ikp = 0; L.sr = 0;
             }
         B2_END
         group_sync<C>(grp);
@@ -187,6 +188,8 @@ void group_proc(const KParams& P, BlockSmem<C>& sm, int grp, int nk, int bx,
             npmax = nk_ > npmax ? nk_ : npmax;
         }
         npmax *= nbp;
+        constexpr bool sr_op = SR;   // erfc = Coulomb - erf: every primitive quartet is visited twice (omega < 0)
+        if (sr_op) npmax *= 2;
 
         for (int ip = 0; ip < npmax; ip++) {
             // ---- phase A: Rys roots
@@ -195,7 +198,8 @@ void group_proc(const KParams& P, BlockSmem<C>& sm, int grp, int nk, int bx,
                 if (L.valid) {
                     SlotSmem<C>& s = sm.slot[L.slot];
                     if (s.active && L.ibp < nbp)
-                        phase_roots<C>(s, L.t.g, sm.bprim[L.ibp], s.kprim[L.ikp], P.tb, P.omega);
+                        phase_roots<C>(s, L.t.g, sm.bprim[L.ibp], s.kprim[L.ikp], P.tb,
+                                       sr_op ? (L.sr ? -P.omega : 0.0) : P.omega, (sr_op && L.sr) ? -1.0 : 1.0);
                 }
             B2_END
             group_sync<C>(grp);
@@ -215,7 +219,8 @@ void group_proc(const KParams& P, BlockSmem<C>& sm, int grp, int nk, int bx,
                     SlotSmem<C>& s = sm.slot[L.slot];
                     if (s.active && L.ibp < nbp) {
                         phase_accumulate<C>(s, L.t, sm.bra.ABx, sm.bra.ABy, sm.bra.ABz);
-                        if (++L.ikp == s.nprim_k) { L.ikp = 0; L.ibp++; }
+                        if (sr_op && !L.sr) L.sr = 1;
+                        else { L.sr = 0; if (++L.ikp == s.nprim_k) { L.ikp = 0; L.ibp++; } }
                     }
                 }
             B2_END
@@ -236,7 +241,7 @@ void group_proc(const KParams& P, BlockSmem<C>& sm, int grp, int nk, int bx,
     }
 }
 
-template <class C>
+template <class C, bool SR>
 #ifdef __CUDACC__
 __device__ __forceinline__
 #else
@@ -318,10 +323,10 @@ void jk_block(const KParams& P, int bx, int by, BlockSmem<C>& sm)
         atomicAdd(&P.counters[0], (unsigned long long)nk);
         atomicAdd(&P.counters[1], (unsigned long long)(kend - kbeg - nk));
     }
-    group_proc<C>(P, sm, threadIdx.x / GC::TG, nk, bx, ctx);
+    group_proc<C, SR>(P, sm, threadIdx.x / GC::TG, nk, bx, ctx);
 #else
     if (P.counters) { P.counters[0] += nk; P.counters[1] += kend - kbeg - nk; }
-    for (int grp = 0; grp < GC::NG; grp++) group_proc<C>(P, sm, grp, nk, bx, ctxs);
+    for (int grp = 0; grp < GC::NG; grp++) group_proc<C, SR>(P, sm, grp, nk, bx, ctxs);
 #endif
 
     // ---- flush the register-resident J[ij] of the stationary bra pair

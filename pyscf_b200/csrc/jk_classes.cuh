@@ -49,19 +49,19 @@ struct ClassCfg {
 };
 
 #ifndef B200JK_EMULATE
-template <class C>
+template <class C, bool SR>
 __global__ void __launch_bounds__(TpqCfg<C>::NT) jk_tpq_kernel(const KParams P)
 {
     const int bx = blockIdx.x * P.shard_world + P.shard_rank;
-    if (bx < P.nbra) tpq_block<C>(P, bx, blockIdx.y, blockIdx.z);
+    if (bx < P.nbra) tpq_block<C, SR>(P, bx, blockIdx.y, blockIdx.z);
 }
-template <class C>
+template <class C, bool SR>
 __global__ void __launch_bounds__(GroupCfg<C>::NT) jk_class_kernel(const KParams P)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     BlockSmem<C>& sm = *reinterpret_cast<BlockSmem<C>*>(smraw);
     const int bx = blockIdx.x * P.shard_world + P.shard_rank;
-    if (bx < P.nbra) jk_block<C>(P, bx, blockIdx.y, sm);
+    if (bx < P.nbra) jk_block<C, SR>(P, bx, blockIdx.y, sm);
 }
 #endif
 
@@ -69,6 +69,24 @@ __global__ void __launch_bounds__(GroupCfg<C>::NT) jk_class_kernel(const KParams
 typedef cudaStream_t b2_stream_t;
 #else
 typedef int b2_stream_t;
+#endif
+
+#ifndef B200JK_EMULATE
+template <class C, bool SR>
+void launch_block_kernel(const KParams& P, dim3 grid, int nt, size_t smem, b2_stream_t st)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(jk_class_kernel<C, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+        // leave half of the 228 KB for L1 (Rys tables, density blocks); the other half lets several CTAs co-reside
+        cudaFuncSetAttribute(jk_class_kernel<C, SR>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+        configured = true;
+    }
+    jk_class_kernel<C, SR><<<grid, nt, smem, st>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw std::runtime_error(std::string("jk_class_kernel launch: ") + cudaGetErrorString(e));
+}
 #endif
 
 template <int LI, int LJ, int LK, int LL>
@@ -83,14 +101,18 @@ void launch_one(KParams P, b2_stream_t st)
         int ny = (P.nket + P.kchunk - 1) / P.kchunk;
 #ifndef B200JK_EMULATE
         dim3 grid(nbx, ny, (P.bra_nprim_max + TpqCfg<C>::PSLICE - 1) / TpqCfg<C>::PSLICE);
-        jk_tpq_kernel<C><<<grid, TpqCfg<C>::NT, 0, st>>>(P);
+        if (P.omega < 0.0) jk_tpq_kernel<C, true><<<grid, TpqCfg<C>::NT, 0, st>>>(P);   // erfc operator: two root sets
+        else jk_tpq_kernel<C, false><<<grid, TpqCfg<C>::NT, 0, st>>>(P);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) throw std::runtime_error(std::string("jk_tpq_kernel launch: ") + cudaGetErrorString(e));
 #else
         (void)st;
         for (int bx = P.shard_rank; bx < P.nbra; bx += P.shard_world)
             for (int by = 0; by < ny; by++)
-                for (int bz = 0; bz * TpqCfg<C>::PSLICE < P.bra_nprim_max; bz++) tpq_block<C>(P, bx, by, bz);
+                for (int bz = 0; bz * TpqCfg<C>::PSLICE < P.bra_nprim_max; bz++) {
+                    if (P.omega < 0.0) tpq_block<C, true>(P, bx, by, bz);
+                    else tpq_block<C, false>(P, bx, by, bz);
+                }
 #endif
         return;
     }
@@ -98,24 +120,18 @@ void launch_one(KParams P, b2_stream_t st)
     P.kchunk = pick_kchunk(nbx, P.nket, Cfg::GC::NSLOT, KCH_MAX);
     int ny = (P.nket + P.kchunk - 1) / P.kchunk;
 #ifndef B200JK_EMULATE
-    static bool configured = false;
     size_t smem = sizeof(BlockSmem<C>);
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(jk_class_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-        // leave half of the 228 KB for L1 (Rys tables, density blocks); the other half lets several CTAs co-reside
-        cudaFuncSetAttribute(jk_class_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
-        configured = true;
-    }
     dim3 grid(nbx, ny);
-    jk_class_kernel<C><<<grid, Cfg::NT, smem, st>>>(P);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) throw std::runtime_error(std::string("jk_class_kernel launch: ") + cudaGetErrorString(e));
+    if (P.omega < 0.0) launch_block_kernel<C, true>(P, grid, Cfg::NT, smem, st);   // erfc operator: two root sets per primitive quartet
+    else launch_block_kernel<C, false>(P, grid, Cfg::NT, smem, st);
 #else
     (void)st;
     BlockSmem<C>* sm = new BlockSmem<C>();
     for (int bx = P.shard_rank; bx < P.nbra; bx += P.shard_world)
-        for (int by = 0; by < ny; by++) jk_block<C>(P, bx, by, *sm);
+        for (int by = 0; by < ny; by++) {
+            if (P.omega < 0.0) jk_block<C, true>(P, bx, by, *sm);
+            else jk_block<C, false>(P, bx, by, *sm);
+        }
     delete sm;
 #endif
 }

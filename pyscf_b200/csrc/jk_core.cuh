@@ -18,9 +18,11 @@
 #ifdef __CUDACC__
 #define B2_HD __host__ __device__ __forceinline__
 #define B2_UNROLL _Pragma("unroll")
+#define B2_NOUNROLL _Pragma("unroll 1")
 #else
 #define B2_HD inline __attribute__((always_inline))
 #define B2_UNROLL
+#define B2_NOUNROLL
 #endif
 
 namespace b200jk {
@@ -234,7 +236,8 @@ B2_HD void slot_set_cd(SlotSmem<C>& s, double CDx, double CDy, double CDz)
 // Phase A: Rys roots for primitive quartet (bp, kp).  Threads g, g+G, ... < NR of the slot.
 // PrimPair::cc carries sqrt(2 pi^2.5) c_i c_j K_ij / p, so the ERI prefactor is cc_b cc_k / sqrt(p+q).
 template <class C>
-B2_HD void phase_roots(SlotSmem<C>& s, int g, const PrimPair& bp, const PrimPair& kp, const RysTables& tb, double omega)
+B2_HD void phase_roots(SlotSmem<C>& s, int g, const PrimPair& bp, const PrimPair& kp, const RysTables& tb, double omega,
+                       double wsign = 1.0)
 {
     double p = bp.p, q = kp.p;
     double PQx = bp.Px - kp.Px, PQy = bp.Py - kp.Py, PQz = bp.Pz - kp.Pz;
@@ -243,7 +246,7 @@ B2_HD void phase_roots(SlotSmem<C>& s, int g, const PrimPair& bp, const PrimPair
     double ipq = rs * rs;
     double rho = p * q * ipq;
     double x = rho * (PQx * PQx + PQy * PQy + PQz * PQz);
-    double pref = bp.cc * kp.cc * rs;
+    double pref = bp.cc * kp.cc * rs * wsign;
     double theta = 1.0;
     if (omega > 0.0) {  // erf(omega r)/r: evaluate at x*theta, u*theta, w*sqrt(theta)
         theta = omega * omega / (omega * omega + rho);
@@ -505,9 +508,15 @@ B2_HD double schwarz_pair(int la, int lb, const ShellPair& sp, const PrimPair* p
             double rho = p * q * ipq;
             double x = rho * (PQ[0] * PQ[0] + PQ[1] * PQ[1] + PQ[2] * PQ[2]);
             double pref = bp.cc * kq.cc / sqrt(pq);
-            double theta = 1.0;
-            if (omega > 0.0) { theta = omega * omega / (omega * omega + rho); x *= theta; pref *= sqrt(theta); }
-            for (int r = 0; r < nr; r++) {
+            // omega < 0: erfc(|omega| r)/r = 1/r - erf(|omega| r)/r, i.e. a second root set with negated weights
+            const double x0 = x, pref0 = pref;
+            for (int r2 = 0; r2 < (omega < 0.0 ? 2 * nr : nr); r2++) {
+                const int r = r2 % nr;
+                double theta = 1.0;
+                x = x0; pref = pref0;
+                const double om = (omega < 0.0) ? (r2 >= nr ? -omega : 0.0) : omega;
+                if (om > 0.0) { theta = om * om / (om * om + rho); x *= theta; pref *= sqrt(theta); }
+                if (r2 >= nr) pref = -pref;
                 double u, w;
                 rys_root(tb, nr, r, x, u, w);
                 u *= theta; w *= pref;

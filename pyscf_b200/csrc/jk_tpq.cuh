@@ -76,7 +76,7 @@ B2_HD void tpq_g2d(double c00, double c0p, double b00, double b10, double b01, d
 }
 
 // all Cartesian integrals of one shell quartet: v[(d*NK + c)*NAB + b*NI + a]
-template <class C>
+template <class C, bool SR>
 B2_HD void tpq_eri(const KParams& P, const ShellPair& bp, const ShellPair& kp, int ib0, int ib1, double* v)
 {
     using T = TpqCfg<C>;
@@ -93,16 +93,24 @@ B2_HD void tpq_eri(const KParams& P, const ShellPair& bp, const ShellPair& kp, i
             double ipq = rs * rs;
             double rho = p * q * ipq;
             double x = rho * (PQx * PQx + PQy * PQy + PQz * PQz);
-            double pref = b.cc * k.cc * rs;
-            double theta = 1.0;
-            if (P.omega > 0.0) {
-                theta = P.omega * P.omega / (P.omega * P.omega + rho);
-                x *= theta;
-                pref *= sqrt(theta);
-            }
+            const double x0 = x, pref0 = b.cc * k.cc * rs;
             double hip = 0.5 / p, hiq = 0.5 / q;
             if (C::LB == 0) hip = 0.0;
             if (C::LT == 0) hiq = 0.0;
+            // omega < 0 (erfc = Coulomb - erf): a second pass over the roots with the erf-attenuated set, weights negated
+            constexpr int nsr = SR ? 2 : 1;
+            B2_NOUNROLL
+            for (int sr = 0; sr < nsr; sr++) {
+            double pref = pref0;
+            double theta = 1.0;
+            const double om = (nsr == 2) ? (sr ? -P.omega : 0.0) : P.omega;
+            x = x0;
+            if (om > 0.0) {
+                theta = om * om / (om * om + rho);
+                x *= theta;
+                pref *= sqrt(theta);
+            }
+            if (sr) pref = -pref;
             B2_UNROLL
             for (int r = 0; r < C::NR; r++) {
                 double u, w;
@@ -136,6 +144,7 @@ B2_HD void tpq_eri(const KParams& P, const ShellPair& bp, const ShellPair& kp, i
                         }
                     }
                 }
+            }
             }
         }
     }
@@ -235,7 +244,7 @@ B2_HD void tpq_digest(const KParams& P, const double* v, double f, int i0, int j
     }
 }
 
-template <class C>
+template <class C, bool SR>
 #ifdef __CUDACC__
 __device__ __forceinline__
 #else
@@ -278,7 +287,7 @@ void tpq_block(const KParams& P, int bx, int by, int bz)
             if (kp.same) f *= 0.5;
             if (P.same_class && kk == bx) f *= 0.5;
             double v[T::NOUT];
-            tpq_eri<C>(P, bpair, kp, ib0, ib1, v);
+            tpq_eri<C, SR>(P, bpair, kp, ib0, ib1, v);
             tpq_digest<C>(P, v, f, bpair.i0, bpair.j0, kp.i0, kp.j0, jij);
         }
 #if defined(__CUDA_ARCH__)
