@@ -19,6 +19,8 @@
  *                            -> lib.hermi_triu                   pyscf/lib/numpy_helper.py:499
  *   b200jk_df_build          incore.cholesky_eri                 pyscf/df/incore.py:129-220
  *                            -> GTOnr3c_drv / GTOint2c           pyscf/lib/gto/fill_nr_3c.c:196, fill_int2c.c:36
+ *   b200jk_df_prepare_j /    df_jk.get_j (integral-direct J, no tensor)  pyscf/df/df_jk.py:415-506
+ *   b200jk_df_direct_j       -> CVHFnr3c2e_* passes over int3c2e  pyscf/lib/vhf/optimizer.c:305-370
  *   b200jk_df_jk             df_jk.get_jk                        pyscf/df/df_jk.py:280-413
  *                            -> AO2MOnr_e2_drv + NPdgemm         pyscf/lib/ao2mo/nr_ao2mo.c:1240, np_helper/npdot.c:32
  *   b200jk_get_stats         (no reference equivalent; logger.timer 'vj and vk' pyscf/scf/hf.py:2158)
@@ -67,6 +69,13 @@ int b200jk_direct_jk_device(b200jk_handle h, const double* dm_dev, int n_dm, int
 /* Density fitting: aux tables are a second libcint-layout set for the auxiliary basis. */
 int b200jk_df_build(b200jk_handle h, const int32_t* aux_atm, int aux_natm, const int32_t* aux_bas, int aux_nbas,
                     const double* aux_env, int aux_nenv, double omega, double lindep);
+/* Integral-direct DF-J (df_jk.get_j, pyscf/df/df_jk.py:415-506; what DF.get_jk does for with_k=False while no tensor
+ * exists, df_jk.py:282-285).  prepare_j = auxiliary tables + factorised metric (the reference's cached dfobj._vjopt);
+ * direct_j = two passes over the 3-center integrals: rho = j2c^-1 (P|ij) D_ji, then J_ij = (ij|P) rho_P.  No tensor is
+ * stored; b200jk_df_direct_j also works after b200jk_df_build.  dm, vj: host [n_dm, nao, nao]. */
+int b200jk_df_prepare_j(b200jk_handle h, const int32_t* aux_atm, int aux_natm, const int32_t* aux_bas, int aux_nbas,
+                        const double* aux_env, int aux_nenv, double omega, double lindep);
+int b200jk_df_direct_j(b200jk_handle h, const double* dm, int n_dm, int nao, double* vj);
 /* occ_coeff: [n_dm, nao, nocc] = C_occ*sqrt(occ) (may be NULL -> general-dm K algorithm). */
 int b200jk_df_jk(b200jk_handle h, const double* dm, int n_dm, int nao, const double* occ_coeff, int nocc, int hermi,
                  double* vj, double* vk);

@@ -52,6 +52,10 @@ struct DFState {
     int build_rank = 0, build_world = 1, row0 = 0, nrow = 0;   // rows [row0, row0+nrow) of the tensor live on this rank
     double* d_cderi = nullptr;
     double omega = 0.0;
+    // metric factor kept for the integral-direct J (df_jk.get_j): Cholesky L (GPU: column-major lower, emulation: row-major
+    // lower) or, when the metric is not positive definite, W = diag(w)^-1/2 V^T [naux, naux_sph] row-major
+    double *d_fac = nullptr, *d_W = nullptr;
+    bool fac_chol = true;
     // J/K workspaces
     double *d_dmtril = nullptr, *d_rho = nullptr, *d_vjtril = nullptr, *d_A = nullptr, *d_Y = nullptr, *d_occ = nullptr,
            *d_dm = nullptr, *d_vk = nullptr, *d_vj = nullptr;
@@ -77,7 +81,7 @@ void df_free(DFState* d)
     dev_free(d->d_acart_sh); dev_free(d->d_acart_comp); dev_free(d->d_asph_sh); dev_free(d->d_asph_m);
     dev_free(d->d_ash_l); dev_free(d->d_ash_cart); dev_free(d->d_ash_sph);
     for (int c = 0; c < NPC; c++) dev_free(d->d_ao_off[c]);
-    dev_free(d->d_pairoff); dev_free(d->d_cderi);
+    dev_free(d->d_pairoff); dev_free(d->d_cderi); dev_free(d->d_fac); dev_free(d->d_W);
     dev_free(d->d_dmtril); dev_free(d->d_rho); dev_free(d->d_vjtril); dev_free(d->d_A); dev_free(d->d_Y); dev_free(d->d_occ);
     dev_free(d->d_dm); dev_free(d->d_vk); dev_free(d->d_vj); dev_free(d->d_Y2); dev_free(d->d_occT);
 #ifndef B200JK_EMULATE
@@ -334,8 +338,47 @@ void cpu_cholesky_lower(std::vector<double>& a, int n, bool& ok)
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-extern "C" int b200jk_df_build(b200jk_handle h, const int32_t* aux_atm, int aux_natm, const int32_t* aux_bas, int aux_nbas,
-                               const double* aux_env, int aux_nenv, double omega, double lindep)
+// (ij|P) for all AO shell pairs in batches of bounded scratch: Cartesian rows d_xc[naux_cart, cols] -> spherical aux rows
+// d_xa[naux_sph, cols]; use(col0, cols) consumes one batch (columns = Cartesian pair blocks, DFState::ao_off_h).
+template <class F>
+static void for_each_j3c_batch(b200jk_handle h, DFState* d, double omega, stream_t st, F use)
+{
+    const int nac = d->naux_cart, nas = d->naux_sph;
+    const int64_t budget_cols = std::max<int64_t>(4096, (int64_t)((3ULL << 30) / ((size_t)nac * 8)));
+    double* d_xc = (double*)dev_alloc((size_t)nac * (size_t)std::min<int64_t>(budget_cols + 128, d->rowlen) * 8);
+    double* d_xa = (double*)dev_alloc((size_t)nas * (size_t)std::min<int64_t>(budget_cols + 128, d->rowlen) * 8);
+    for (int cb = 0; cb < NPC; cb++) {
+        const auto& offs = d->ao_off_h[cb];
+        const int np_all = (int)h->pc[cb].all.size();
+        if (np_all == 0) continue;
+        const int64_t blk = (int64_t)ncart(h->pc[cb].la) * ncart(h->pc[cb].lb);
+        int p0 = 0;
+        while (p0 < np_all) {
+            int p1 = (int)std::min<int64_t>(np_all, p0 + std::max<int64_t>(1, budget_cols / blk));
+            const int64_t col0 = offs[p0], cols = (int64_t)(p1 - p0) * blk;
+            for (int lk = 0; lk <= LMAX; lk++) {
+                if (d->akets[lk].empty()) continue;
+                J3cParams P{};
+                P.bra_pairs = h->pc[cb].d_all + p0; P.nbra = p1 - p0; P.bra_out_off = d->d_ao_off[cb] + p0;
+                P.ket_shells = d->d_akets[lk]; P.nket = (int)d->akets[lk].size();
+                P.bra_prims = h->d_prims; P.ket_prims = d->d_aprims;
+                P.tb = h->tb; P.omega = omega; P.out = d_xc; P.row_stride = cols; P.col0 = col0;
+                launch_j3c(cb, lk, P, st);
+            }
+            AuxC2SFn a2 {d_xc, d_xa, cols, nas, d->d_asph_sh, d->d_asph_m, d->d_ash_l, d->d_ash_cart, h->d_c2s_off, h->d_c2s};
+            launch_1d((long)nas * cols, a2, st);
+            use(col0, cols, d_xa);
+            p0 = p1;
+        }
+    }
+#ifndef B200JK_EMULATE
+    CK(cudaStreamSynchronize(st));
+#endif
+    dev_free(d_xc); dev_free(d_xa);
+}
+
+static int df_build_impl(b200jk_handle h, const int32_t* aux_atm, int aux_natm, const int32_t* aux_bas, int aux_nbas,
+                         const double* aux_env, int aux_nenv, double omega, double lindep, bool j_only)
 {
     if (!h) return 1;
     try {
@@ -438,6 +481,7 @@ extern "C" int b200jk_df_build(b200jk_handle h, const int32_t* aux_atm, int aux_
             dev_free(d_info);
             // keep the factor in d_j2c (column-major lower == row-major upper of the same symmetric storage)
             if (use_chol) CK(cudaMemcpyAsync(d_j2c, d_chol, (size_t)nas * nas * 8, cudaMemcpyDeviceToDevice, st));
+            else { d->d_W = (double*)dev_alloc((size_t)std::max(nkeep, 1) * nas * 8); h2d(d->d_W, W.data(), (size_t)nkeep * nas * 8, st); CK(cudaStreamSynchronize(st)); }
             dev_free(d_chol);
         }
 #else
@@ -449,10 +493,21 @@ extern "C" int b200jk_df_build(b200jk_handle h, const int32_t* aux_atm, int aux_
             cpu_cholesky_lower(Lm, nas, ok);
             if (!ok) throw std::runtime_error("emulation: metric not positive definite (eig fallback is GPU-only)");
             j2c_h = Lm;
+            memcpy(d_j2c, Lm.data(), (size_t)nas * nas * 8);   // emulation: row-major lower factor
         }
         (void)lindep;
 #endif
         d->naux = nkeep;
+        d->fac_chol = use_chol;
+        d->d_fac = d_j2c;
+        if (j_only) {   // integral-direct J only (b200jk_df_prepare_j): no tensor
+#ifndef B200JK_EMULATE
+            CK(cudaStreamSynchronize(st));
+#endif
+            dev_free(d_j2c_cart);
+            d->row0 = 0; d->nrow = 0;
+            return 0;
+        }
 
         // ---- rows of the metric transform owned by this rank: T[nloc][nas] (rows of L^-1, or of W = diag(w)^-1/2 V^T)
         const int bw = h->shard_world, br = h->shard_rank;
@@ -494,51 +549,23 @@ extern "C" int b200jk_df_build(b200jk_handle h, const int32_t* aux_atm, int aux_
         // ---- (ij|P) in batches of AO shell pairs (bounded scratch): Cartesian rows -> spherical aux -> T . (P|ij)
         const long npair = d->npair;
         double* d_ycart = (double*)dev_alloc((size_t)std::max(nloc, 1) * d->rowlen * 8);
-        const int64_t budget_cols = std::max<int64_t>(4096, (int64_t)((3ULL << 30) / ((size_t)nac * 8)));
-        double* d_xc = (double*)dev_alloc((size_t)nac * (size_t)std::min<int64_t>(budget_cols + 128, d->rowlen) * 8);
-        double* d_xa = (double*)dev_alloc((size_t)nas * (size_t)std::min<int64_t>(budget_cols + 128, d->rowlen) * 8);
-        for (int cb = 0; cb < NPC; cb++) {
-            const auto& offs = d->ao_off_h[cb];
-            const int np_all = (int)h->pc[cb].all.size();
-            if (np_all == 0) continue;
-            const int64_t blk = (int64_t)ncart(h->pc[cb].la) * ncart(h->pc[cb].lb);
-            int p0 = 0;
-            while (p0 < np_all) {
-                int p1 = (int)std::min<int64_t>(np_all, p0 + std::max<int64_t>(1, budget_cols / blk));
-                const int64_t col0 = offs[p0], cols = (int64_t)(p1 - p0) * blk;
-                for (int lk = 0; lk <= LMAX; lk++) {
-                    if (d->akets[lk].empty()) continue;
-                    J3cParams P{};
-                    P.bra_pairs = h->pc[cb].d_all + p0; P.nbra = p1 - p0; P.bra_out_off = d->d_ao_off[cb] + p0;
-                    P.ket_shells = d->d_akets[lk]; P.nket = (int)d->akets[lk].size();
-                    P.bra_prims = h->d_prims; P.ket_prims = d->d_aprims;
-                    P.tb = h->tb; P.omega = omega; P.out = d_xc; P.row_stride = cols; P.col0 = col0;
-                    launch_j3c(cb, lk, P, st);
-                }
-                AuxC2SFn a2 {d_xc, d_xa, cols, nas, d->d_asph_sh, d->d_asph_m, d->d_ash_l, d->d_ash_cart, h->d_c2s_off, h->d_c2s};
-                launch_1d((long)nas * cols, a2, st);
-                if (nloc > 0) {
+        for_each_j3c_batch(h, d, omega, st, [&](int64_t col0, int64_t cols, const double* d_xa) {
+            if (nloc <= 0) return;
 #ifndef B200JK_EMULATE
-                    // row-major Y[nloc, cols] (ld rowlen) = T[nloc, nas] . Xa[nas, cols]  <=>  col-major Y^T = Xa^T . T^T
-                    const double one = 1.0, zero = 0.0;
-                    CKB(cublasDgemm(d->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)cols, nloc, nas, &one, d_xa, (int)cols, d_T, nas, &zero,
-                                    d_ycart + col0, (int)d->rowlen));
+            // row-major Y[nloc, cols] (ld rowlen) = T[nloc, nas] . Xa[nas, cols]  <=>  col-major Y^T = Xa^T . T^T
+            const double one = 1.0, zero = 0.0;
+            CKB(cublasDgemm(d->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)cols, nloc, nas, &one, d_xa, (int)cols, d_T, nas, &zero,
+                            d_ycart + col0, (int)d->rowlen));
 #else
-                    for (int i = 0; i < nloc; i++)
-                        for (int64_t c = 0; c < cols; c++) {
-                            double acc = 0.0;
-                            for (int k = 0; k < nas; k++) acc += d_T[(size_t)i * nas + k] * d_xa[(size_t)k * cols + c];
-                            d_ycart[(size_t)i * d->rowlen + col0 + c] = acc;
-                        }
-#endif
+            for (int i = 0; i < nloc; i++)
+                for (int64_t c = 0; c < cols; c++) {
+                    double acc = 0.0;
+                    for (int k = 0; k < nas; k++) acc += d_T[(size_t)i * nas + k] * d_xa[(size_t)k * cols + c];
+                    d_ycart[(size_t)i * d->rowlen + col0 + c] = acc;
                 }
-                p0 = p1;
-            }
-        }
-#ifndef B200JK_EMULATE
-        CK(cudaStreamSynchronize(st));
 #endif
-        dev_free(d_xc); dev_free(d_xa); dev_free(d_T);
+        });
+        dev_free(d_T);
         d->d_cderi = (double*)dev_alloc((size_t)std::max(nloc, 1) * npair * 8);
         PairC2SFn p2 {d_ycart, d->d_cderi, d->rowlen, npair, nsh, d->d_pairoff, h->d_sph_sh, h->d_sph_m, h->d_sh_l, h->d_c2s_off, h->d_c2s};
         launch_1d((long)nloc * npair, p2, st);
@@ -546,7 +573,164 @@ extern "C" int b200jk_df_build(b200jk_handle h, const int32_t* aux_atm, int aux_
         CK(cudaStreamSynchronize(st));
 #endif
         dev_free(d_ycart);
-        dev_free(d_j2c_cart); dev_free(d_j2c);
+        dev_free(d_j2c_cart);
+    } catch (std::exception& e) { set_err(h, e.what()); return 2; }
+    return 0;
+}
+
+extern "C" int b200jk_df_build(b200jk_handle h, const int32_t* aux_atm, int aux_natm, const int32_t* aux_bas, int aux_nbas,
+                               const double* aux_env, int aux_nenv, double omega, double lindep)
+{
+    return df_build_impl(h, aux_atm, aux_natm, aux_bas, aux_nbas, aux_env, aux_nenv, omega, lindep, false);
+}
+
+// Integral-direct DF-J without the tensor (df_jk.get_j, pyscf/df/df_jk.py:415-506): prepare = auxiliary tables + metric
+// factor (the reference's cached dfobj._vjopt with its cho_factor'ed j2c) ...
+extern "C" int b200jk_df_prepare_j(b200jk_handle h, const int32_t* aux_atm, int aux_natm, const int32_t* aux_bas, int aux_nbas,
+                                   const double* aux_env, int aux_nenv, double omega, double lindep)
+{
+    return df_build_impl(h, aux_atm, aux_natm, aux_bas, aux_nbas, aux_env, aux_nenv, omega, lindep, true);
+}
+
+namespace {
+// Dc[s][off + b*NI + a] = D_cart[i0+a][j0+b] (+ transpose element for off-diagonal shell pairs; D_cart is symmetric)
+struct PairGatherFn {
+    const ShellPair* pairs; const int64_t* off; int ni, nj, ncart_; const double* dcart; double* dc; int64_t rowlen;
+    B2_HD void operator()(long idx) const
+    {
+        const int blk = ni * nj;
+        long s = idx / ((long)npairs * blk), r = idx - s * (long)npairs * blk;
+        long p = r / blk; int e = (int)(r - p * blk);
+        int b = e / ni, a = e - b * ni;
+        const ShellPair& sp = pairs[p];
+        double v = dcart[(size_t)s * ncart_ * ncart_ + (size_t)(sp.i0 + a) * ncart_ + sp.j0 + b];
+        dc[(size_t)s * rowlen + off[p] + e] = (sp.ish == sp.jsh) ? v : 2.0 * v;
+    }
+    int npairs;
+};
+// Jacc_cart[s][i0+a][j0+b] = w Jc[s][off + b*NI + a], w = 1/2 on diagonal shell pairs (J = Jacc + Jacc^T afterwards)
+struct PairScatterFn {
+    const ShellPair* pairs; const int64_t* off; int ni, nj, ncart_; const double* jc; double* jcart; int64_t rowlen; int npairs;
+    B2_HD void operator()(long idx) const
+    {
+        const int blk = ni * nj;
+        long s = idx / ((long)npairs * blk), r = idx - s * (long)npairs * blk;
+        long p = r / blk; int e = (int)(r - p * blk);
+        int b = e / ni, a = e - b * ni;
+        const ShellPair& sp = pairs[p];
+        double v = jc[(size_t)s * rowlen + off[p] + e];
+        jcart[(size_t)s * ncart_ * ncart_ + (size_t)(sp.i0 + a) * ncart_ + sp.j0 + b] = (sp.ish == sp.jsh) ? 0.5 * v : v;
+    }
+};
+}  // namespace
+
+// ... and the two passes over the 3-center integrals:  rho = j2c^-1 (P|ij) D_ji ,  J_ij = (ij|P) rho_P
+extern "C" int b200jk_df_direct_j(b200jk_handle h, const double* dm, int n_dm, int nao, double* vj)
+{
+    if (!h) return 1;
+    try {
+        DFState* d = h->df;
+        if (!d || !d->d_fac) throw std::runtime_error("call b200jk_df_prepare_j (or b200jk_df_build) before b200jk_df_direct_j");
+        if (nao != h->nsph) throw std::runtime_error("nao does not match the basis of this handle");
+        if (n_dm < 1 || !dm || !vj) throw std::runtime_error("bad arguments");
+        auto t0 = std::chrono::steady_clock::now();
+#ifndef B200JK_EMULATE
+        CK(cudaSetDevice(h->device));
+        cudaStream_t st = h->stream;
+        CKB(cublasSetStream(d->cublas, st));
+        CKS(cusolverDnSetStream(d->cusolver, st));
+#else
+        stream_t st = 0;
+#endif
+        const int nas = d->naux_sph, nc = h->ncart, ns = h->nsph;
+        const size_t ns2 = (size_t)ns * ns, nc2 = (size_t)nc * nc;
+        double* d_dsph = (double*)dev_alloc(ns2 * n_dm * 8);
+        double* d_dcart = (double*)dev_alloc(nc2 * n_dm * 8);
+        double* d_dc = (double*)dev_alloc((size_t)d->rowlen * n_dm * 8);
+        double* d_rho = (double*)dev_alloc((size_t)nas * n_dm * 8);
+        h2d(d_dsph, dm, ns2 * n_dm * 8, st);
+        Sph2CartFn s2c{d_dsph, d_dcart, ns, nc, 0, h->d_cart_sh, h->d_cart_comp, h->d_sh_l, h->d_sh_sph, h->d_c2s_off, h->d_c2s};
+        launch_1d((long)nc2 * n_dm, s2c, st);
+        for (int cb = 0; cb < NPC; cb++) {
+            const int np = (int)h->pc[cb].all.size();
+            if (!np) continue;
+            PairGatherFn g{h->pc[cb].d_all, d->d_ao_off[cb], ncart(h->pc[cb].la), ncart(h->pc[cb].lb), nc, d_dcart, d_dc, d->rowlen, np};
+            launch_1d((long)n_dm * np * g.ni * g.nj, g, st);
+        }
+        dev_zero(d_rho, (size_t)nas * n_dm * 8, st);
+        // ---- pass 1: rho[s][P] = sum_col (P|col) Dc[s][col]
+        for_each_j3c_batch(h, d, d->omega, st, [&](int64_t col0, int64_t cols, const double* d_xa) {
+#ifndef B200JK_EMULATE
+            const double one = 1.0;
+            CKB(cublasDgemm(d->cublas, CUBLAS_OP_T, CUBLAS_OP_N, nas, n_dm, (int)cols, &one, d_xa, (int)cols, d_dc + col0, (int)d->rowlen,
+                            &one, d_rho, nas));
+#else
+            for (int s = 0; s < n_dm; s++)
+                for (int P = 0; P < nas; P++) {
+                    double acc = 0.0;
+                    for (int64_t c = 0; c < cols; c++) acc += d_xa[(size_t)P * cols + c] * d_dc[(size_t)s * d->rowlen + col0 + c];
+                    d_rho[(size_t)s * nas + P] += acc;
+                }
+#endif
+        });
+        // ---- solve the metric equation  (cho_solve / the eigen-decomposed inverse)
+#ifndef B200JK_EMULATE
+        if (d->fac_chol) {
+            int* d_info = (int*)dev_alloc(4);
+            CKS(cusolverDnDpotrs(d->cusolver, CUBLAS_FILL_MODE_LOWER, nas, n_dm, d->d_fac, nas, d_rho, nas, d_info));
+            int info = 0;
+            d2h(&info, d_info, 4, st);
+            CK(cudaStreamSynchronize(st));
+            dev_free(d_info);
+            if (info != 0) throw std::runtime_error("potrs failed");
+        } else {
+            const int nk = d->naux;
+            double* d_tmp = (double*)dev_alloc((size_t)std::max(nk, 1) * n_dm * 8);
+            const double one = 1.0, zero = 0.0;
+            CKB(cublasDgemm(d->cublas, CUBLAS_OP_T, CUBLAS_OP_N, nk, n_dm, nas, &one, d->d_W, nas, d_rho, nas, &zero, d_tmp, nk));
+            CKB(cublasDgemm(d->cublas, CUBLAS_OP_N, CUBLAS_OP_N, nas, n_dm, nk, &one, d->d_W, nas, d_tmp, nk, &zero, d_rho, nas));
+            CK(cudaStreamSynchronize(st));
+            dev_free(d_tmp);
+        }
+#else
+        for (int s = 0; s < n_dm; s++) {   // L L^T x = b with the row-major lower factor
+            double* x = d_rho + (size_t)s * nas;
+            const double* L = d->d_fac;
+            for (int i = 0; i < nas; i++) { double a = x[i]; for (int k = 0; k < i; k++) a -= L[(size_t)i * nas + k] * x[k]; x[i] = a / L[(size_t)i * nas + i]; }
+            for (int i = nas - 1; i >= 0; i--) { double a = x[i]; for (int k = i + 1; k < nas; k++) a -= L[(size_t)k * nas + i] * x[k]; x[i] = a / L[(size_t)i * nas + i]; }
+        }
+#endif
+        // ---- pass 2: Jc[s][col] = sum_P (P|col) rho[s][P]
+        double* d_jc = d_dc;   // reuse
+        for_each_j3c_batch(h, d, d->omega, st, [&](int64_t col0, int64_t cols, const double* d_xa) {
+#ifndef B200JK_EMULATE
+            const double one = 1.0, zero = 0.0;
+            CKB(cublasDgemm(d->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)cols, n_dm, nas, &one, d_xa, (int)cols, d_rho, nas, &zero,
+                            d_jc + col0, (int)d->rowlen));
+#else
+            for (int s = 0; s < n_dm; s++)
+                for (int64_t c = 0; c < cols; c++) {
+                    double acc = 0.0;
+                    for (int P = 0; P < nas; P++) acc += d_xa[(size_t)P * cols + c] * d_rho[(size_t)s * nas + P];
+                    d_jc[(size_t)s * d->rowlen + col0 + c] = acc;
+                }
+#endif
+        });
+        dev_zero(d_dcart, nc2 * n_dm * 8, st);
+        for (int cb = 0; cb < NPC; cb++) {
+            const int np = (int)h->pc[cb].all.size();
+            if (!np) continue;
+            PairScatterFn g{h->pc[cb].d_all, d->d_ao_off[cb], ncart(h->pc[cb].la), ncart(h->pc[cb].lb), nc, d_jc, d_dcart, d->rowlen, np};
+            launch_1d((long)n_dm * np * g.ni * g.nj, g, st);
+        }
+        Cart2SphFn c2s{d_dcart, d_dsph, ns, nc, 1.0, 0, h->d_sph_sh, h->d_sph_m, h->d_sh_l, h->d_sh_cart, h->d_c2s_off, h->d_c2s};
+        launch_1d((long)ns2 * n_dm, c2s, st);
+        d2h(vj, d_dsph, ns2 * n_dm * 8, st);
+#ifndef B200JK_EMULATE
+        CK(cudaStreamSynchronize(st));
+#endif
+        dev_free(d_dsph); dev_free(d_dcart); dev_free(d_dc); dev_free(d_rho);
+        h->stats.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     } catch (std::exception& e) { set_err(h, e.what()); return 2; }
     return 0;
 }

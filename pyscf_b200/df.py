@@ -26,6 +26,7 @@ class DF:
         self._libpath = libpath
         self.shard = shard         # (rank, world): build only this rank's auxiliary rows (multi-GPU, see parallel.py)
         self._handle = None
+        self._vjopt = None         # handle holding only the factorised metric (integral-direct J, get_j)
         self._rsh_df = {}          # omega -> DF (pyscf/df/df.py:298-333 range_coulomb)
         self.omega = None
         self.lindep = 1e-7         # pyscf/df/incore.py:30-33 LINEAR_DEP_THR
@@ -71,7 +72,10 @@ class DF:
         self.auxmol = None
         if self._handle is not None:
             self._handle.close()
+        if getattr(self, '_vjopt', None) is not None:
+            self._vjopt.close()
         self._handle = None
+        self._vjopt = None
         self._rsh_df = {}
         return self
 
@@ -114,9 +118,46 @@ class DF:
         return self._rsh_df[key]
 
     # ---- J/K -----------------------------------------------------------------------------------------
+    def _prepare_j(self):
+        """Auxiliary tables + factorised metric only (the reference's cached dfobj._vjopt, df_jk.py:422-455)."""
+        mol = self.mol
+        if self.auxmol is None:
+            self.auxmol = make_auxmol(mol, self.auxbasis)
+        aux = self.auxmol
+        h = _lib.Handle(mol._atm, mol._bas, np.array(mol._env, dtype=np.float64), device=self.device,
+                        libpath=self._libpath)
+        atm = np.ascontiguousarray(aux._atm, dtype=np.int32)
+        bas = np.ascontiguousarray(aux._bas, dtype=np.int32)
+        env = np.ascontiguousarray(aux._env, dtype=np.float64)
+        omega = 0.0 if self.omega is None else float(self.omega)
+        h.check(h.lib.b200jk_df_prepare_j(h._h, _lib.iptr(atm), len(atm), _lib.iptr(bas), len(bas), _lib.dptr(env),
+                                          len(env), omega, self.lindep), 'b200jk_df_prepare_j')
+        self._vjopt = h
+        self.nao = int(mol.ao_loc_nr(cart=False)[-1])
+        return h
+
+    def get_j(self, dm, hermi=0, direct_scf_tol=1e-13):
+        """Integral-direct J without the three-index tensor: rho = j2c^-1 (P|ij) D_ji, J_ij = (ij|P) rho_P, two passes
+        over the 3-center integrals on the GPU (df_jk.get_j, pyscf/df/df_jk.py:415-506)."""
+        h = self._handle or getattr(self, '_vjopt', None) or self._prepare_j()
+        nao = self.nao
+        dm = np.asarray(dm)
+        if dm.shape[-1] != nao or dm.shape[-2] != nao:
+            raise RuntimeError('dm shape %s does not match nao=%d' % (dm.shape, nao))
+        if np.iscomplexobj(dm):
+            return self.get_j(dm.real, hermi, direct_scf_tol) + 1j * self.get_j(dm.imag, hermi, direct_scf_tol)
+        shape = dm.shape
+        dms = np.ascontiguousarray(dm.reshape(-1, nao, nao), dtype=np.float64)
+        vj = np.empty_like(dms)
+        h.check(h.lib.b200jk_df_direct_j(h._h, _lib.dptr(dms), len(dms), nao, _lib.dptr(vj)), 'b200jk_df_direct_j')
+        return vj.reshape(shape)
+
     def get_jk(self, dm, hermi=1, with_j=True, with_k=True, direct_scf_tol=1e-13, omega=None):
         if omega is not None and omega != 0 and omega != self.omega:
             return self.range_coulomb(omega).get_jk(dm, hermi, with_j, with_k, direct_scf_tol)
+        if not with_k and self._handle is None and self.shard is None:
+            # J only and no tensor yet: integral-direct J (pyscf/df/df_jk.py:282-285)
+            return self.get_j(dm, hermi, direct_scf_tol), None
         if self._handle is None:
             self.build()
         mo_coeff = getattr(dm, 'mo_coeff', None)
@@ -166,19 +207,22 @@ class TaggedDM(np.ndarray):
         self.mo_occ = getattr(obj, 'mo_occ', None)
 
 
-def density_fit(mf, auxbasis=None, device=0):
-    """Install a B200 DF object as mf.with_df (pyscf/df/df_jk.py:31-107 does the same with df.DF)."""
+def density_fit(mf, auxbasis=None, device=0, only_dfj=False):
+    """Install a B200 DF object as mf.with_df (pyscf/df/df_jk.py:31-107 does the same with df.DF).  With
+    only_dfj=True J comes from the fitted tensor and K from the 4-center kernels (RIJONX; _DFHF.get_jk,
+    pyscf/df/df_jk.py:150-179)."""
     mf.with_df = DF(mf.mol, auxbasis, device=device)
+    mf.only_dfj = only_dfj
     return mf
 
 
-def smoke():
-    from . import gto
-    from oracle import oracle as O
-    mol = gto.M(atom='O 0 0 0; H 0 -0.757 0.587; H 0 0.757 0.587', basis='cc-pvdz')
-    dfobj = DF(mol, 'weigend').build()
-    np.random.seed(1)
-    dms = np.random.random((2, mol.nao, mol.nao))
-    vj, vk = dfobj.get_jk(dms, hermi=0)
-    print('smoke: DF J/K fp', O.fp(vj), O.fp(vk), '(reference -194.15910890730066, -46.365071587653517)')
-    assert abs(O.fp(vj) - (-194.15910890730066)) < 1e-8 and abs(O.fp(vk) - (-46.365071587653517)) < 1e-8
+def get_jk_only_dfj(with_df, mol, dm, hermi=1, with_j=True, with_k=True, omega=None, direct_scf_tol=1e-13, vhfopt=None):
+    """_DFHF.get_jk with only_dfj=True (pyscf/df/df_jk.py:157-179): vj from the DF object, vk from the exact
+    4-center path of jk.get_jk."""
+    from . import jk as _jk
+    vj = vk = None
+    if with_j:
+        vj = with_df.get_jk(dm, hermi, True, False, direct_scf_tol, omega)[0]
+    if with_k:
+        vk = _jk.get_jk(mol, dm, hermi, vhfopt, False, True, omega)[1]
+    return vj, vk

@@ -29,7 +29,8 @@ _libs = {}
 SYMBOLS = ['b200jk_create', 'b200jk_destroy', 'b200jk_set_screening', 'b200jk_direct_jk', 'b200jk_direct_jk_device',
            'b200jk_df_build', 'b200jk_df_jk', 'b200jk_df_naux', 'b200jk_get_q_cond', 'b200jk_get_stats',
            'b200jk_last_error', 'b200jk_version', 'b200jk_set_stream', 'b200jk_fp64_peak',
-           'b200jk_set_profile', 'b200jk_get_class_times', 'b200jk_df_get_cderi', 'b200jk_i8gemm_test', 'b200jk_df_set_kmode', 'b200jk_set_shard', 'b200jk_df_jk_device', 'b200jk_df_local_rows']
+           'b200jk_set_profile', 'b200jk_get_class_times', 'b200jk_df_get_cderi', 'b200jk_i8gemm_test', 'b200jk_df_set_kmode', 'b200jk_set_shard', 'b200jk_df_jk_device', 'b200jk_df_local_rows',
+           'b200jk_df_prepare_j', 'b200jk_df_direct_j']
 
 
 def load(path=None):
@@ -49,6 +50,9 @@ def load(path=None):
     lib.b200jk_direct_jk_device.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
     lib.b200jk_df_build.argtypes = [vp, c_int_p, ctypes.c_int, c_int_p, ctypes.c_int, c_double_p, ctypes.c_int,
                                     ctypes.c_double, ctypes.c_double]
+    lib.b200jk_df_prepare_j.argtypes = [vp, c_int_p, ctypes.c_int, c_int_p, ctypes.c_int, c_double_p, ctypes.c_int,
+                                        ctypes.c_double, ctypes.c_double]
+    lib.b200jk_df_direct_j.argtypes = [vp, c_double_p, ctypes.c_int, ctypes.c_int, c_double_p]
     lib.b200jk_df_jk.argtypes = [vp, c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_int,
                                  c_double_p, c_double_p]
     lib.b200jk_df_naux.argtypes = [vp, ctypes.POINTER(ctypes.c_int)]

@@ -55,6 +55,49 @@ def test_df_emulated_long_range(emu_lib):
     assert abs(vj - rj).max() < 1e-8 and abs(vk - rk).max() < 1e-8
 
 
+def _check_direct_j(libpath):
+    # integral-direct J (no tensor; df_jk.get_j, pyscf/df/df_jk.py:415-506) == J from the stored tensor;
+    # reference fingerprint of the DF J matrix, pyscf/df/test/test_df_jk.py:151
+    mol = gto.M(atom=H2O, basis='cc-pvdz')
+    d = DF(mol, 'weigend', libpath=libpath)
+    nao = mol.nao
+    np.random.seed(1)
+    dms = np.random.random((2, nao, nao))
+    vj, vk = d.get_jk(dms, hermi=0, with_k=False)
+    assert vk is None and d._handle is None          # no tensor was built
+    assert abs(O.fp(vj) - (-194.15910890730066)) < 1e-9
+    ref, _ = O.cholesky_eri(mol, make_auxmol(mol, 'weigend'))
+    rj, _ = O.df_get_jk(ref, nao, dms)
+    assert abs(vj - rj).max() < 1e-10
+    # f orbital shells / g auxiliary shells, one non-symmetric density
+    mol = gto.M(atom='He 0 0 0; Ne 1.2 0.3 0', basis='cc-pvtz')
+    d = DF(mol, 'def2-universal-jkfit', libpath=libpath)
+    dm = np.random.random((mol.nao, mol.nao))
+    vj = d.get_j(dm)
+    vj2 = d.build().get_jk(dm, hermi=0, with_k=False)[0]
+    assert abs(vj - vj2).max() < 1e-9
+    # RIJONX (only_dfj): J fitted, K exact (_DFHF.get_jk, pyscf/df/df_jk.py:157-179)
+    from pyscf_b200.df import get_jk_only_dfj
+    from pyscf_b200.jk import VHFOpt
+    mol = gto.M(atom=H2O, basis='6-31g')
+    d = DF(mol, 'weigend', libpath=libpath)
+    dm = np.random.random((mol.nao, mol.nao))
+    dm = dm + dm.T
+    vj, vk = get_jk_only_dfj(d, mol, dm, vhfopt=VHFOpt(mol, libpath=libpath))
+    ref, nao = O.cholesky_eri(mol, make_auxmol(mol, 'weigend'))
+    assert abs(vj - O.df_get_jk(ref, nao, dm)[0]).max() < 1e-10
+    assert abs(vk - O.get_jk(mol, dm)[1]).max() < 1e-10
+
+
+def test_df_direct_j_emulated(emu_lib):
+    _check_direct_j(emu_lib)
+
+
+@pytest.mark.gpu
+def test_df_direct_j_gpu():
+    _check_direct_j(None)
+
+
 @pytest.mark.gpu
 def test_df_gpu_h2o():
     _check_h2o(None)
