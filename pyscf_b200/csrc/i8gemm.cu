@@ -78,10 +78,18 @@ void gemm_ar(const SliceStack& A, int a_row0, int M, const SliceStack& B, double
     if (A.Kp != B.Kp || A.ns != B.ns) throw std::runtime_error("i8gemm_ar: operand stacks disagree");
     if (A.ns * AR_BN > 512) throw std::runtime_error("i8gemm_ar: too many slices for TMEM");
     static bool configured = false;
+    static int nsm = 148;
     if (!configured) {
-        CK(cudaFuncSetAttribute(i8gemm_ar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(i8gemm_ar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM_MAX));
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
         configured = true;
     }
+    static const int nsa_env = getenv("B200JK_AR_NSA") ? atoi(getenv("B200JK_AR_NSA")) : 0;   // tuning: A ring depth
+    int nsa = AR_MAXA;
+    while (nsa > 2 && ar_smem_bytes(nsa, A.ns) > AR_SMEM_MAX) nsa--;
+    if (nsa_env >= 2 && nsa_env < nsa) nsa = nsa_env;
     CUtensorMap ta, tb;
     make_tmap(&ta, A.q, (uint64_t)A.ns * A.Rp, A.Kp, BM);
     make_tmap(&tb, B.q, (uint64_t)B.ns * B.Rp, B.Kp, AR_BN);
@@ -90,8 +98,11 @@ void gemm_ar(const SliceStack& A, int a_row0, int M, const SliceStack& B, double
     P.Ea = A.E; P.Eb = B.E; P.C = C; P.ldc = ldc; P.inner = inner; P.a_row0 = a_row0; P.ksplit = 1; P.dbg = nullptr;
     static const int stack = getenv("B200JK_AR_STACK") ? atoi(getenv("B200JK_AR_STACK")) : 1;   // 0: one slice pair per MMA (tuning yardstick)
     P.stack = stack;
-    dim3 grid((B.R + AR_BN - 1) / AR_BN, (M + BM - 1) / BM);
-    i8gemm_ar_kernel<<<grid, NTHREADS, AR_SMEM_BYTES, st>>>(ta, tb, P);
+    P.nsa = nsa;
+    const int ntiles = ((B.R + AR_BN - 1) / AR_BN) * ((M + BM - 1) / BM);
+    static const int persist = getenv("B200JK_AR_PERSIST") ? atoi(getenv("B200JK_AR_PERSIST")) : 1;   // 0: one tile per CTA (yardstick)
+    dim3 grid(persist ? std::min(ntiles, nsm) : ntiles);
+    i8gemm_ar_kernel<<<grid, NTHREADS, ar_smem_bytes(nsa, A.ns), st>>>(ta, tb, P);
     CK(cudaGetLastError());
 }
 

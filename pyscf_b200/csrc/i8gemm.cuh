@@ -46,6 +46,7 @@ struct GemmParams {
     int ksplit;            // K blocks are divided among gridDim.z CTAs (fp64 reductions make this safe)
     long long* dbg;        // optional cycle stamps of CTA (0,0) (tests/tuning)
     int stack;             // i8gemm_ar_kernel: multiply A_k with up to 4 stacked B slices per MMA (N = 256)
+    int nsa;               // i8gemm_ar_kernel: depth of the A ring (host: as many 16 KB stages as fit in 227 KB)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -297,40 +298,50 @@ i8gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
 // ---------------------------------------------------------------------------------------------- GEMM kernel, "all groups resident"
 // Variant for a SHORT contraction (K = nao) and a narrow N (stage 1 of DF-K: N = nocc): tile 128 x 64 with ALL slice-pair
 // groups resident in TMEM (group g at columns g*64, ns*64 <= 512).  The A_k tile is loaded ONCE per (K block, k) and
-// reused for every B_l (A-stationary: no operand re-reads), and there is ONE epilogue that combines the groups in
+// reused for every B_l (A-stationary: no operand re-reads), and there is ONE epilogue per tile that combines the groups in
 // fp64 registers and stores each output once (no read-modify-write, no zero fill).
+// Persistent: one CTA per SM walks over the tiles (N tile fastest, so the CTAs that share an A tile run side by side
+// and meet in L2).  The TMA producer keeps prefetching the next tile's operands while the epilogue drains TMEM; the
+// accumulators are handed back to the MMA warp as soon as the last tcgen05.ld has landed, before the stores.
 constexpr int AR_BN = 64;
-constexpr int AR_NSA = 4, AR_NSB = 2;            // A ring: one slice tile per stage; B ring: ALL slices of a K block per stage
-constexpr int AR_A_BYTES = BM * BK, AR_B1_BYTES = AR_BN * BK, AR_B_BYTES = MAXS * AR_B1_BYTES;
-constexpr int AR_SMEM_BYTES = AR_NSA * AR_A_BYTES + AR_NSB * AR_B_BYTES + 4 * EPI_STAGE_INTS * 4 + 1024 + 512;
+constexpr int AR_NSB = 2;                        // B ring: ALL slices of a K block per stage
+constexpr int AR_MAXA = 8;                       // A ring: one slice tile per stage, depth chosen by the host (P.nsa)
+constexpr int AR_A_BYTES = BM * BK, AR_B1_BYTES = AR_BN * BK;
+constexpr int AR_BAR_BYTES = 512, AR_EPI_BYTES = 4 * EPI_STAGE_INTS * 4;
+constexpr int AR_SMEM_MAX = 232448;              // 227 KB opt-in limit per CTA
+__host__ __device__ constexpr int ar_smem_bytes(int nsa, int ns) { return nsa * AR_A_BYTES + AR_NSB * ns * AR_B1_BYTES + AR_BAR_BYTES + AR_EPI_BYTES + 1024; }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const GemmParams P)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int ns = P.ns, nsa = P.nsa;
+    const int bstage = ns * AR_B1_BYTES;
     uint8_t* sA = smem;
-    uint8_t* sB = smem + AR_NSA * AR_A_BYTES;
-    uint64_t* bars = (uint64_t*)(smem + AR_NSA * AR_A_BYTES + AR_NSB * AR_B_BYTES);
-    uint64_t* afull = bars;                      // [AR_NSA]
-    uint64_t* aempty = afull + AR_NSA;
-    uint64_t* bfull = aempty + AR_NSA;           // [AR_NSB]
+    uint8_t* sB = smem + nsa * AR_A_BYTES;
+    uint64_t* bars = (uint64_t*)(sB + AR_NSB * bstage);
+    uint64_t* afull = bars;                      // [AR_MAXA]
+    uint64_t* aempty = afull + AR_MAXA;
+    uint64_t* bfull = aempty + AR_MAXA;          // [AR_NSB]
     uint64_t* bempty = bfull + AR_NSB;
-    uint64_t* tfull = bempty + AR_NSB;           // [1]
-    uint32_t* tmem_slot = (uint32_t*)(tfull + 1);
-    int* epi_stage = (int*)(smem + AR_NSA * AR_A_BYTES + AR_NSB * AR_B_BYTES + 512);
+    uint64_t* tfull = bempty + AR_NSB;           // [1] accumulators complete (MMA -> epilogue)
+    uint64_t* tempty = tfull + 1;                // [1] accumulators drained  (epilogue -> MMA), 4 arrivals
+    uint32_t* tmem_slot = (uint32_t*)(tempty + 1);
+    int* epi_stage = (int*)((uint8_t*)bars + AR_BAR_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mt = blockIdx.y, nt = blockIdx.x;
     const int nkb = P.Kp / BK;
-    const int ns = P.ns;
+    const int ntn = (P.N + AR_BN - 1) / AR_BN, ntm = (P.M + BM - 1) / BM;
+    const int ntiles = ntn * ntm;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmapA);
         prefetch_tmap(&tmapB);
-        for (int i = 0; i < AR_NSA; i++) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+        for (int i = 0; i < nsa; i++) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
         for (int i = 0; i < AR_NSB; i++) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
         mbar_init(tfull, 1);
+        mbar_init(tempty, 4);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -342,105 +353,122 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
     if (warp == 0) {
         if (lane == 0) {
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-            for (int kb = 0; kb < nkb; kb++) {
-                mbar_wait(&bempty[sb], pb ^ 1);
-                mbar_expect_tx(&bfull[sb], ns * AR_B1_BYTES);
-                for (int l = 0; l < ns; l++)
-                    tma_load_2d(sB + sb * AR_B_BYTES + l * AR_B1_BYTES, &tmapB, &bfull[sb], kb * BK, l * P.Np + nt * AR_BN);
-                if (++sb == AR_NSB) { sb = 0; pb ^= 1; }
-                for (int k = 0; k < ns; k++) {
-                    mbar_wait(&aempty[sa], pa ^ 1);
-                    mbar_expect_tx(&afull[sa], AR_A_BYTES);
-                    tma_load_2d(sA + sa * AR_A_BYTES, &tmapA, &afull[sa], kb * BK, k * P.Mp + P.a_row0 + mt * BM);
-                    if (++sa == AR_NSA) { sa = 0; pa ^= 1; }
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int mt = tile / ntn, nt = tile - mt * ntn;
+                for (int kb = 0; kb < nkb; kb++) {
+                    mbar_wait(&bempty[sb], pb ^ 1);
+                    mbar_expect_tx(&bfull[sb], ns * AR_B1_BYTES);
+                    for (int l = 0; l < ns; l++)
+                        tma_load_2d(sB + sb * bstage + l * AR_B1_BYTES, &tmapB, &bfull[sb], kb * BK, l * P.Np + nt * AR_BN);
+                    if (++sb == AR_NSB) { sb = 0; pb ^= 1; }
+                    for (int k = 0; k < ns; k++) {
+                        mbar_wait(&aempty[sa], pa ^ 1);
+                        mbar_expect_tx(&afull[sa], AR_A_BYTES);
+                        tma_load_2d(sA + sa * AR_A_BYTES, &tmapA, &afull[sa], kb * BK, k * P.Mp + P.a_row0 + mt * BM);
+                        if (++sa == nsa) { sa = 0; pa ^= 1; }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-            for (int kb = 0; kb < nkb; kb++) {
-                mbar_wait(&bfull[sb], pb);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+                mbar_wait(tempty, (uint32_t)((it & 1) ^ 1));     // the epilogue has read the previous tile out of TMEM
                 tc_fence_after();
-                const uint32_t bbase = smem_u32(sB + sb * AR_B_BYTES);
-                for (int k = 0; k < ns; k++) {
-                    mbar_wait(&afull[sa], pa);
+                for (int kb = 0; kb < nkb; kb++) {
+                    mbar_wait(&bfull[sb], pb);
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(sA + sa * AR_A_BYTES);
-                    // The B slices l = 0..ns-1-k of this K block lie back to back in shared memory (64 rows x 128 B each),
-                    // i.e. they ARE one K-major tile of (ns-k)*64 rows, and their groups k+l are adjacent TMEM column
-                    // blocks: one MMA with N = 64*cnt multiplies A_k with cnt slices at once.  A 128-row MMA costs the
-                    // same ~128 cycles for any N <= 256, so stacking cuts the 28 slice-pair MMAs per K block to 10.
-                    const int lstep = P.stack ? 4 : 1;
-                    for (int l = 0; l < ns - k; l += lstep) {
-                        const int cnt = (ns - k - l < lstep) ? ns - k - l : lstep;
-                        const uint32_t idesc_n = make_idesc_i8(BM, cnt * AR_BN);
-                        const uint32_t b0 = bbase + l * AR_B1_BYTES;
-                        const uint32_t tacc = tmem_base + (k + l) * AR_BN;
-                        uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;   // first touch of group k+l is (kb=0, k=0)
+                    const uint32_t bbase = smem_u32(sB + sb * bstage);
+                    for (int k = 0; k < ns; k++) {
+                        mbar_wait(&afull[sa], pa);
+                        tc_fence_after();
+                        const uint32_t a0 = smem_u32(sA + sa * AR_A_BYTES);
+                        // The B slices l = 0..ns-1-k of this K block lie back to back in shared memory (64 rows x 128 B each),
+                        // i.e. they ARE one K-major tile of (ns-k)*64 rows, and their groups k+l are adjacent TMEM column
+                        // blocks: one MMA with N = 64*cnt multiplies A_k with cnt slices at once.  A 128-row MMA costs the
+                        // same ~128 cycles for any N <= 256, so stacking cuts the 28 slice-pair MMAs per K block to 10.
+                        const int lstep = P.stack ? 4 : 1;
+                        for (int l = 0; l < ns - k; l += lstep) {
+                            const int cnt = (ns - k - l < lstep) ? ns - k - l : lstep;
+                            const uint32_t idesc_n = make_idesc_i8(BM, cnt * AR_BN);
+                            const uint32_t b0 = bbase + l * AR_B1_BYTES;
+                            const uint32_t tacc = tmem_base + (k + l) * AR_BN;
+                            uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;   // first touch of group k+l is (kb=0, k=0)
 #pragma unroll
-                        for (int kk = 0; kk < BK / UK; kk++) {
-                            mma_i8(tacc, make_desc_k_sw128(a0 + kk * UK), make_desc_k_sw128(b0 + kk * UK), idesc_n, acc);
-                            acc = 1;
+                            for (int kk = 0; kk < BK / UK; kk++) {
+                                mma_i8(tacc, make_desc_k_sw128(a0 + kk * UK), make_desc_k_sw128(b0 + kk * UK), idesc_n, acc);
+                                acc = 1;
+                            }
                         }
+                        mma_commit(&aempty[sa]);
+                        if (++sa == nsa) { sa = 0; pa ^= 1; }
                     }
-                    mma_commit(&aempty[sa]);
-                    if (++sa == AR_NSA) { sa = 0; pa ^= 1; }
+                    mma_commit(&bempty[sb]);
+                    if (++sb == AR_NSB) { sb = 0; pb ^= 1; }
                 }
-                mma_commit(&bempty[sb]);
-                if (++sb == AR_NSB) { sb = 0; pb ^= 1; }
+                mma_commit(tfull);
             }
-            mma_commit(tfull);
         }
     } else {
         const int q = warp & 3;
         int* stg = epi_stage + q * EPI_STAGE_INTS;
-        const int mrow0 = mt * BM + q * 32;
-        mbar_wait(tfull, 0);
-        tc_fence_after();
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+            const int mt = tile / ntn, nt = tile - mt * ntn;
+            const int mrow0 = mt * BM + q * 32;
+            mbar_wait(tfull, (uint32_t)(it & 1));
+            tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < AR_BN; c0 += 32) {
-            const int n = nt * AR_BN + c0 + lane;
-            if (nt * AR_BN + c0 >= P.N) break;
-            // combine the groups in fp64 (smallest weight first), row = this lane
-            double accv[32];
+            for (int c0 = 0; c0 < AR_BN; c0 += 32) {
+                const int n = nt * AR_BN + c0 + lane;
+                const bool chunk_on = nt * AR_BN + c0 < P.N;
+                // combine the groups in fp64 (smallest weight first), row = this lane
+                double accv[32];
 #pragma unroll
-            for (int j = 0; j < 32; j++) accv[j] = 0.0;
-            for (int g = ns - 1; g >= 0; g--) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + g * AR_BN + c0, r);
-                const double w = pow2i(-12 - 7 * g);
+                for (int j = 0; j < 32; j++) accv[j] = 0.0;
+                if (chunk_on) {
+                    for (int g = ns - 1; g >= 0; g--) {
+                        uint32_t r[32];
+                        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + g * AR_BN + c0, r);
+                        const double w = pow2i(-12 - 7 * g);
 #pragma unroll
-                for (int j = 0; j < 32; j++) accv[j] += (double)(int)r[j] * w;
-            }
-            // transpose through shared memory in two 32-bit halves so that a warp stores one output row segment
-            const bool ncol_ok = n < P.N;
-            const int ebn = ncol_ok ? P.Eb[n] : 0;
-            unsigned int lo[32], hi[32];
+                        for (int j = 0; j < 32; j++) accv[j] += (double)(int)r[j] * w;
+                    }
+                }
+                if (c0 + 32 >= AR_BN) {   // last read of this tile's accumulators: hand TMEM back before the stores
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty);
+                }
+                if (!chunk_on) continue;
+                // transpose through shared memory in two 32-bit halves so that a warp stores one output row segment
+                const bool ncol_ok = n < P.N;
+                const int ebn = ncol_ok ? P.Eb[n] : 0;
+                unsigned int lo[32], hi[32];
 #pragma unroll
-            for (int j = 0; j < 32; j++) stg[lane * 33 + j] = (int)(__double_as_longlong(accv[j]) & 0xffffffffLL);
-            __syncwarp();
+                for (int j = 0; j < 32; j++) stg[lane * 33 + j] = (int)(__double_as_longlong(accv[j]) & 0xffffffffLL);
+                __syncwarp();
 #pragma unroll
-            for (int rr = 0; rr < 32; rr++) lo[rr] = (unsigned int)stg[rr * 33 + lane];
-            __syncwarp();
+                for (int rr = 0; rr < 32; rr++) lo[rr] = (unsigned int)stg[rr * 33 + lane];
+                __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; j++) stg[lane * 33 + j] = (int)(__double_as_longlong(accv[j]) >> 32);
-            __syncwarp();
+                for (int j = 0; j < 32; j++) stg[lane * 33 + j] = (int)(__double_as_longlong(accv[j]) >> 32);
+                __syncwarp();
 #pragma unroll
-            for (int rr = 0; rr < 32; rr++) hi[rr] = (unsigned int)stg[rr * 33 + lane];
-            __syncwarp();
-            double outv[32];
+                for (int rr = 0; rr < 32; rr++) hi[rr] = (unsigned int)stg[rr * 33 + lane];
+                __syncwarp();
 #pragma unroll
-            for (int rr = 0; rr < 32; rr++) outv[rr] = __longlong_as_double(((long long)hi[rr] << 32) | (long long)lo[rr]);
-#pragma unroll
-            for (int rr = 0; rr < 32; rr++) {
-                const int m = mrow0 + rr;
-                if (ncol_ok && m < P.M) {
-                    const double v = outv[rr] * pow2i(P.Ea[P.a_row0 + m] + ebn);
-                    double* dst;
-                    if (P.inner > 0) dst = P.C + (long)(m % P.inner) * P.ldc + (long)(m / P.inner) * P.N + n;
-                    else dst = P.C + (long)m * P.ldc + n;
-                    *dst = v;
+                for (int rr = 0; rr < 32; rr++) {
+                    const int m = mrow0 + rr;
+                    if (ncol_ok && m < P.M) {
+                        const double v = __longlong_as_double(((long long)hi[rr] << 32) | (long long)lo[rr]) * pow2i(P.Ea[P.a_row0 + m] + ebn);
+                        double* dst;
+                        if (P.inner > 0) dst = P.C + (long)(m % P.inner) * P.ldc + (long)(m / P.inner) * P.N + n;
+                        else dst = P.C + (long)m * P.ldc + n;
+                        *dst = v;
+                    }
                 }
             }
         }

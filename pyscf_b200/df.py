@@ -110,10 +110,11 @@ class DF:
     def range_coulomb(self, omega):
         key = float(omega)
         if key not in self._rsh_df:
-            rsh = DF(self.mol, self.auxbasis, device=self.device, libpath=self._libpath)
+            rsh = DF(self.mol, self.auxbasis, device=self.device, libpath=self._libpath, shard=self.shard)
             rsh.auxmol = self.auxmol
             rsh.omega = key
             rsh.lindep = self.lindep
+            rsh.k_engine, rsh.k_slices = self.k_engine, self.k_slices
             self._rsh_df[key] = rsh.build()
         return self._rsh_df[key]
 

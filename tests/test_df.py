@@ -135,3 +135,32 @@ def test_df_gpu_benzene_properties():
     from pyscf_b200.jk import VHFOpt
     ej, ek = VHFOpt(mol).get_jk(a)
     assert abs(ja - ej).max() < 0.1 and abs(ka - ek).max() < 0.1   # fitting error of def2-svp-jkfit, elements O(100)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,geom,basis', [('gly4_dz', 'gly4', 'cc-pvdz'), ('bz_tz_df', 'benzene', 'cc-pvtz')])
+def test_df_golden_vectors(name, geom, basis):
+    """Oracle-generated fixtures (tools/make_golden_df.py): (Gly)4/cc-pVDZ is config 5's chemistry at oracle size (aux up
+    to f), benzene/cc-pVTZ has f orbital and g auxiliary shells.  Tensor rows, fingerprint of the whole tensor, J and K
+    (both K engines)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'df_%s.npz' % name))
+    mol = gto.M(atom=geometry(geom), basis=basis)
+    d = DF(mol).build()
+    assert d.get_naoaux() == int(g['naux'])
+    cderi = d._cderi
+    assert abs(cderi[g['rows']] - g['cderi_rows']).max() < 1e-9
+    assert abs(O.fp(cderi) - float(g['fp_cderi'])) < 1e-8
+    nao = mol.nao
+    np.random.seed(1)
+    dms = np.random.random((2, nao, nao))
+    vj, vk = d.get_jk(dms, hermi=0)
+    assert abs(vj - g['vj']).max() < 1e-9 and abs(vk - g['vk']).max() < 1e-9
+    # occupied-orbital path through both K engines (tcgen05 int8 slices, cuBLAS DGEMM)
+    c = np.linalg.qr(np.random.random((nao, 21)))[0]
+    occ = np.full(21, 2.0)
+    dm = TaggedDM((c * occ).dot(c.T), mo_coeff=c, mo_occ=occ)
+    k_tc = d.set_k_engine('tcgen05').get_jk(dm, with_j=False)[1]
+    k_dg = d.set_k_engine('dgemm').get_jk(dm, with_j=False)[1]
+    k_gen = d.get_jk(np.asarray(dm), hermi=1, with_j=False)[1]
+    assert abs(k_tc - k_dg).max() < 1e-10 and abs(k_tc - k_gen).max() < 1e-10
