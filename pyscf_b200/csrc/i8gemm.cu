@@ -102,7 +102,25 @@ void gemm_ar(const SliceStack& A, int a_row0, int M, const SliceStack& B, double
     const int ntiles = ((B.R + AR_BN - 1) / AR_BN) * ((M + BM - 1) / BM);
     static const int persist = getenv("B200JK_AR_PERSIST") ? atoi(getenv("B200JK_AR_PERSIST")) : 1;   // 0: one tile per CTA (yardstick)
     dim3 grid(persist ? std::min(ntiles, nsm) : ntiles);
+    static const bool dbg = getenv("B200JK_I8_DEBUG") != nullptr;   // cycle stamps of CTA 0 (tuning)
+    static long long* d_dbg = nullptr;
+    static int dbg_left = 2;
+    if (dbg && dbg_left > 0) {
+        if (!d_dbg) d_dbg = (long long*)dev_alloc(64 * 8);
+        dev_zero(d_dbg, 64 * 8, st);
+        P.dbg = d_dbg;
+    }
     i8gemm_ar_kernel<<<grid, NTHREADS, ar_smem_bytes(nsa, A.ns), st>>>(ta, tb, P);
+    if (P.dbg) {
+        long long hd[64];
+        d2h(hd, d_dbg, 64 * 8, st);
+        CK(cudaStreamSynchronize(st));
+        dbg_left--;
+        for (int it = 0; it < 6; it++)
+            fprintf(stderr, "[i8gemm_ar CTA0 tile %d] mma: wait_tmem %lld issue %lld | epi: wait_acc %lld drain %lld store %lld | tile period %lld cycles\n", it,
+                    hd[it * 8 + 1] - hd[it * 8 + 0], hd[it * 8 + 2] - hd[it * 8 + 1], hd[it * 8 + 4] - hd[it * 8 + 3],
+                    hd[it * 8 + 5] - hd[it * 8 + 4], hd[it * 8 + 6] - hd[it * 8 + 5], it ? hd[it * 8 + 6] - hd[(it - 1) * 8 + 6] : 0LL);
+    }
     CK(cudaGetLastError());
 }
 

@@ -251,6 +251,11 @@ i8gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
         int* stg = epi_stage + q * EPI_STAGE_INTS;
         const int mrow0 = mt * BM + q * 32;      // first row of this warp's 32-row band
+        // per-row exponent and output offset of this warp's 32 rows, one row per lane, fetched ONCE: inside the store loop
+        // a load of P.Ea could not be hoisted above the preceding reduction (may alias) and would serialise on L2 latency
+        const int mlane = mrow0 + lane;
+        const int ea_lane = (mlane < P.M) ? P.Ea[P.a_row0 + mlane] : 0;
+        const long off_lane = (P.inner > 0) ? (long)(mlane % P.inner) * P.ldc + (long)(mlane / P.inner) * P.N : (long)mlane * P.ldc;
         int it = 0;
         for (int g = ns - 1; g >= 0; g--, it++) {
             const int buf = it & 1;
@@ -274,12 +279,11 @@ i8gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                 for (int rr = 0; rr < 32; rr++) {
                     const int m = mrow0 + rr;
                     if (m >= P.M) break;
+                    const int ea = __shfl_sync(0xffffffffu, ea_lane, rr);
+                    const long off = __shfl_sync(0xffffffffu, off_lane, rr);
                     if (ncol_ok && (!P.symmetric || n >= m)) {
-                        const double v = (double)stg[rr * 33 + lane] * pow2i(P.Ea[P.a_row0 + m] + ebn + eg);
-                        double* dst;
-                        if (P.inner > 0) dst = P.C + (long)(m % P.inner) * P.ldc + (long)(m / P.inner) * P.N + n;
-                        else dst = P.C + (long)m * P.ldc + n;
-                        atomicAdd(dst, v);   // RED.ADD.F64: no read latency, safe under split-K
+                        const double v = (double)stg[rr * 33 + lane] * pow2i(ea + ebn + eg);
+                        atomicAdd(P.C + off + n, v);   // RED.ADD.F64: no read latency, safe under split-K
                     }
                 }
                 __syncwarp();
@@ -375,8 +379,10 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+                if (P.dbg && blockIdx.x == 0 && it < 6) P.dbg[it * 8 + 0] = clock64();
                 mbar_wait(tempty, (uint32_t)((it & 1) ^ 1));     // the epilogue has read the previous tile out of TMEM
                 tc_fence_after();
+                if (P.dbg && blockIdx.x == 0 && it < 6) P.dbg[it * 8 + 1] = clock64();
                 for (int kb = 0; kb < nkb; kb++) {
                     mbar_wait(&bfull[sb], pb);
                     tc_fence_after();
@@ -409,6 +415,7 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
                     if (++sb == AR_NSB) { sb = 0; pb ^= 1; }
                 }
                 mma_commit(tfull);
+                if (P.dbg && blockIdx.x == 0 && it < 6) P.dbg[it * 8 + 2] = clock64();   // all MMAs of the tile issued
             }
         }
     } else {
@@ -418,8 +425,15 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
             const int mt = tile / ntn, nt = tile - mt * ntn;
             const int mrow0 = mt * BM + q * 32;
+            // exponent and output offset of this warp's 32 rows, one row per lane, fetched once per tile (see i8gemm_kernel)
+            const int mlane = mrow0 + lane;
+            const int ea_lane = (mlane < P.M) ? P.Ea[P.a_row0 + mlane] : 0;
+            const long off_lane = (P.inner > 0) ? (long)(mlane % P.inner) * P.ldc + (long)(mlane / P.inner) * P.N : (long)mlane * P.ldc;
+            const bool stamp = P.dbg && blockIdx.x == 0 && it < 6 && q == 0 && lane == 0;
+            if (stamp) P.dbg[it * 8 + 3] = clock64();
             mbar_wait(tfull, (uint32_t)(it & 1));
             tc_fence_after();
+            if (stamp) P.dbg[it * 8 + 4] = clock64();   // accumulators complete
 #pragma unroll 1
             for (int c0 = 0; c0 < AR_BN; c0 += 32) {
                 const int n = nt * AR_BN + c0 + lane;
@@ -441,6 +455,7 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty);
+                    if (stamp) P.dbg[it * 8 + 5] = clock64();   // TMEM handed back
                 }
                 if (!chunk_on) continue;
                 // transpose through shared memory in two 32-bit halves so that a warp stores one output row segment
@@ -462,15 +477,13 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
 #pragma unroll
                 for (int rr = 0; rr < 32; rr++) {
                     const int m = mrow0 + rr;
-                    if (ncol_ok && m < P.M) {
-                        const double v = __longlong_as_double(((long long)hi[rr] << 32) | (long long)lo[rr]) * pow2i(P.Ea[P.a_row0 + m] + ebn);
-                        double* dst;
-                        if (P.inner > 0) dst = P.C + (long)(m % P.inner) * P.ldc + (long)(m / P.inner) * P.N + n;
-                        else dst = P.C + (long)m * P.ldc + n;
-                        *dst = v;
-                    }
+                    const int ea = __shfl_sync(0xffffffffu, ea_lane, rr);
+                    const long off = __shfl_sync(0xffffffffu, off_lane, rr);
+                    if (ncol_ok && m < P.M)
+                        P.C[off + n] = __longlong_as_double(((long long)hi[rr] << 32) | (long long)lo[rr]) * pow2i(ea + ebn);
                 }
             }
+            if (stamp) P.dbg[it * 8 + 6] = clock64();   // tile stored
         }
     }
     tc_fence_before();
@@ -529,12 +542,21 @@ __global__ void __launch_bounds__(256) split_long_kernel(const double* __restric
     if (mx > 0.0) { frexp(mx, &e); }
     if (blockIdx.x == 0 && threadIdx.x == 0) E[r] = e;
     const double sc = ldexp(1.0, 6 - e);
-    for (long k = k0 + threadIdx.x; k < k1; k += 256) {
-        double rr = (k < K) ? x[k] * sc : 0.0;
+    // 8 consecutive elements per thread: one 64-bit store per slice (a warp writes 256 contiguous bytes per instruction);
+    // k0, k1 and Kp are multiples of 8 (segments of 8192, Kp multiple of 128)
+    for (long k = k0 + threadIdx.x * 8L; k < k1; k += 256 * 8L) {
+        double rr[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) rr[j] = (k + j < K) ? x[k + j] * sc : 0.0;
         for (int s = 0; s < ns; s++) {
-            double qv = rint(rr);
-            out[((long)s * Rp + r) * Kp + k] = (int8_t)(int)qv;
-            rr = (rr - qv) * 128.0;
+            unsigned long long pack = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const double qv = rint(rr[j]);
+                pack |= (unsigned long long)(unsigned char)(int8_t)(int)qv << (8 * j);
+                rr[j] = (rr[j] - qv) * 128.0;
+            }
+            *reinterpret_cast<unsigned long long*>(out + ((long)s * Rp + r) * Kp + k) = pack;
         }
     }
 }
