@@ -162,7 +162,7 @@ i8gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
 {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for SWIZZLE_128B
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still known to be shared memory
     uint8_t* sA = smem;
     uint8_t* sB = smem + NSTAGE * A_STAGE_BYTES;
     uint64_t* bars = (uint64_t*)(smem + NSTAGE * (A_STAGE_BYTES + B_STAGE_BYTES));
@@ -251,11 +251,6 @@ i8gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
         int* stg = epi_stage + q * EPI_STAGE_INTS;
         const int mrow0 = mt * BM + q * 32;      // first row of this warp's 32-row band
-        // per-row exponent and output offset of this warp's 32 rows, one row per lane, fetched ONCE: inside the store loop
-        // a load of P.Ea could not be hoisted above the preceding reduction (may alias) and would serialise on L2 latency
-        const int mlane = mrow0 + lane;
-        const int ea_lane = (mlane < P.M) ? P.Ea[P.a_row0 + mlane] : 0;
-        const long off_lane = (P.inner > 0) ? (long)(mlane % P.inner) * P.ldc + (long)(mlane / P.inner) * P.N : (long)mlane * P.ldc;
         int it = 0;
         for (int g = ns - 1; g >= 0; g--, it++) {
             const int buf = it & 1;
@@ -274,16 +269,19 @@ i8gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                 for (int j = 0; j < 32; j++) stg[lane * 33 + j] = (int)r[j];
                 __syncwarp();
                 const bool ncol_ok = n < P.N;
-                const int ebn = ncol_ok ? P.Eb[n] : 0;
+                const int ebn = ncol_ok ? __ldg(P.Eb + n) : 0;
 #pragma unroll 4
                 for (int rr = 0; rr < 32; rr++) {
                     const int m = mrow0 + rr;
                     if (m >= P.M) break;
-                    const int ea = __shfl_sync(0xffffffffu, ea_lane, rr);
-                    const long off = __shfl_sync(0xffffffffu, off_lane, rr);
                     if (ncol_ok && (!P.symmetric || n >= m)) {
-                        const double v = (double)stg[rr * 33 + lane] * pow2i(ea + ebn + eg);
-                        atomicAdd(P.C + off + n, v);   // RED.ADD.F64: no read latency, safe under split-K
+                        // __ldg: a plain load could not be hoisted above the preceding reduction (possible alias) and the
+                        // 32 rows would serialise on the load latency
+                        const double v = (double)stg[rr * 33 + lane] * pow2i(__ldg(P.Ea + P.a_row0 + m) + ebn + eg);
+                        double* dst;
+                        if (P.inner > 0) dst = P.C + (long)(m % P.inner) * P.ldc + (long)(m / P.inner) * P.N + n;
+                        else dst = P.C + (long)m * P.ldc + n;
+                        atomicAdd(dst, v);   // RED.ADD.F64: no read latency, safe under split-K
                     }
                 }
                 __syncwarp();
@@ -311,7 +309,7 @@ constexpr int AR_BN = 64;
 constexpr int AR_NSB = 2;                        // B ring: ALL slices of a K block per stage
 constexpr int AR_MAXA = 8;                       // A ring: one slice tile per stage, depth chosen by the host (P.nsa)
 constexpr int AR_A_BYTES = BM * BK, AR_B1_BYTES = AR_BN * BK;
-constexpr int AR_BAR_BYTES = 512, AR_EPI_BYTES = 4 * EPI_STAGE_INTS * 4;
+constexpr int AR_BAR_BYTES = 512, AR_EPI_BYTES = 0;   // the epilogue needs no staging: every lane stores its own row
 constexpr int AR_SMEM_MAX = 232448;              // 227 KB opt-in limit per CTA
 __host__ __device__ constexpr int ar_smem_bytes(int nsa, int ns) { return nsa * AR_A_BYTES + AR_NSB * ns * AR_B1_BYTES + AR_BAR_BYTES + AR_EPI_BYTES + 1024; }
 
@@ -319,7 +317,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const GemmParams P)
 {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still known to be shared memory
     const int ns = P.ns, nsa = P.nsa;
     const int bstage = ns * AR_B1_BYTES;
     uint8_t* sA = smem;
@@ -332,7 +330,6 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
     uint64_t* tfull = bempty + AR_NSB;           // [1] accumulators complete (MMA -> epilogue)
     uint64_t* tempty = tfull + 1;                // [1] accumulators drained  (epilogue -> MMA), 4 arrivals
     uint32_t* tmem_slot = (uint32_t*)(tempty + 1);
-    int* epi_stage = (int*)((uint8_t*)bars + AR_BAR_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = P.Kp / BK;
@@ -420,14 +417,13 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
         }
     } else {
         const int q = warp & 3;
-        int* stg = epi_stage + q * EPI_STAGE_INTS;
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
             const int mt = tile / ntn, nt = tile - mt * ntn;
             const int mrow0 = mt * BM + q * 32;
             // exponent and output offset of this warp's 32 rows, one row per lane, fetched once per tile (see i8gemm_kernel)
             const int mlane = mrow0 + lane;
-            const int ea_lane = (mlane < P.M) ? P.Ea[P.a_row0 + mlane] : 0;
+            const int ea_lane = (mlane < P.M) ? __ldg(P.Ea + P.a_row0 + mlane) : 0;
             const long off_lane = (P.inner > 0) ? (long)(mlane % P.inner) * P.ldc + (long)(mlane / P.inner) * P.N : (long)mlane * P.ldc;
             const bool stamp = P.dbg && blockIdx.x == 0 && it < 6 && q == 0 && lane == 0;
             if (stamp) P.dbg[it * 8 + 3] = clock64();
@@ -436,7 +432,6 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
             if (stamp) P.dbg[it * 8 + 4] = clock64();   // accumulators complete
 #pragma unroll 1
             for (int c0 = 0; c0 < AR_BN; c0 += 32) {
-                const int n = nt * AR_BN + c0 + lane;
                 const bool chunk_on = nt * AR_BN + c0 < P.N;
                 // combine the groups in fp64 (smallest weight first), row = this lane
                 double accv[32];
@@ -458,29 +453,15 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
                     if (stamp) P.dbg[it * 8 + 5] = clock64();   // TMEM handed back
                 }
                 if (!chunk_on) continue;
-                // transpose through shared memory in two 32-bit halves so that a warp stores one output row segment
-                const bool ncol_ok = n < P.N;
-                const int ebn = ncol_ok ? P.Eb[n] : 0;
-                unsigned int lo[32], hi[32];
+                // lane = output row (the TMEM lane): its 32 columns are contiguous in C, so every lane streams its own 256 B;
+                // the partial sectors of neighbouring stores merge in L2.  No transpose, no shuffles; the column exponents come
+                // through the read-only path, so they are not ordered behind the stores of the previous row/chunk.
+                if (mlane < P.M) {
+                    const int nb = nt * AR_BN + c0;
+                    double* dst = P.C + off_lane + nb;
 #pragma unroll
-                for (int j = 0; j < 32; j++) stg[lane * 33 + j] = (int)(__double_as_longlong(accv[j]) & 0xffffffffLL);
-                __syncwarp();
-#pragma unroll
-                for (int rr = 0; rr < 32; rr++) lo[rr] = (unsigned int)stg[rr * 33 + lane];
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < 32; j++) stg[lane * 33 + j] = (int)(__double_as_longlong(accv[j]) >> 32);
-                __syncwarp();
-#pragma unroll
-                for (int rr = 0; rr < 32; rr++) hi[rr] = (unsigned int)stg[rr * 33 + lane];
-                __syncwarp();
-#pragma unroll
-                for (int rr = 0; rr < 32; rr++) {
-                    const int m = mrow0 + rr;
-                    const int ea = __shfl_sync(0xffffffffu, ea_lane, rr);
-                    const long off = __shfl_sync(0xffffffffu, off_lane, rr);
-                    if (ncol_ok && m < P.M)
-                        P.C[off + n] = __longlong_as_double(((long long)hi[rr] << 32) | (long long)lo[rr]) * pow2i(ea + ebn);
+                    for (int j = 0; j < 32; j++)
+                        if (nb + j < P.N) dst[j] = accv[j] * pow2i(ea_lane + __ldg(P.Eb + nb + j));
                 }
             }
             if (stamp) P.dbg[it * 8 + 6] = clock64();   // tile stored

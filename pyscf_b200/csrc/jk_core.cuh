@@ -403,6 +403,14 @@ inline void red_add(double* addr, double val) { *addr += val; }
 //   Kacc[ik] += f v D[jl] ; Kacc[il] += f v D[jk] ; Kacc[jk] += f v D[il] ; Kacc[jl] += f v D[ik]
 //                                                                 (K = Kacc +/- Kacc^T)
 // dmj/dmk: [n_dm][n][n] Cartesian; dmj symmetric; dmk symmetric or antisymmetric.
+// read-only density loads: the non-coherent path is not ordered behind the reductions issued earlier, so the compiler
+// may start them early
+#if defined(__CUDA_ARCH__)
+#define B2_LDG(p) __ldg(p)
+#else
+#define B2_LDG(p) (*(p))
+#endif
+
 template <class C>
 B2_HD void phase_digest(const SlotSmem<C>& s, const ThreadCtx<C>& t, int i0, int j0, int n, int n_dm,
                         const double* dmj, const double* dmk, double* vj, double* vk, double* jacc)
@@ -415,7 +423,7 @@ B2_HD void phase_digest(const SlotSmem<C>& s, const ThreadCtx<C>& t, int i0, int
         if (vj) {
             const double* D = dmj + idm * n2;
             double* J = vj + idm * n2;
-            double dkl = 2.0 * f * D[(size_t)kc * n + ld];
+            double dkl = 2.0 * f * B2_LDG(&D[(size_t)kc * n + ld]);
             double jkl = 0.0;
             B2_UNROLL
             for (int bb = 0; bb < C::NJP; bb++) {
@@ -423,7 +431,7 @@ B2_HD void phase_digest(const SlotSmem<C>& s, const ThreadCtx<C>& t, int i0, int
                 for (int a = 0; a < C::NI; a++) {
                     double val = t.v[bb * C::NI + a];
                     size_t ij = (size_t)(i0 + a) * n + (j0 + b0 + bb);
-                    jkl += val * D[ij];
+                    jkl += val * B2_LDG(&D[ij]);
                     if (jacc) jacc[bb * C::NI + a] += val * dkl;  // stationary bra pair: flushed once per CTA
                     else red_add(&J[ij], val * dkl);
                 }
@@ -439,13 +447,13 @@ B2_HD void phase_digest(const SlotSmem<C>& s, const ThreadCtx<C>& t, int i0, int
             B2_UNROLL
             for (int a = 0; a < C::NI; a++) {
                 kik[a] = 0.0; kil[a] = 0.0;
-                dik[a] = D[(size_t)(i0 + a) * n + kc];
-                dil[a] = D[(size_t)(i0 + a) * n + ld];
+                dik[a] = B2_LDG(&D[(size_t)(i0 + a) * n + kc]);
+                dil[a] = B2_LDG(&D[(size_t)(i0 + a) * n + ld]);
             }
             B2_UNROLL
             for (int bb = 0; bb < C::NJP; bb++) {
                 int jb = j0 + b0 + bb;
-                double djl = D[(size_t)jb * n + ld], djk = D[(size_t)jb * n + kc];
+                double djl = B2_LDG(&D[(size_t)jb * n + ld]), djk = B2_LDG(&D[(size_t)jb * n + kc]);
                 double sjk = 0.0, sjl = 0.0;
                 B2_UNROLL
                 for (int a = 0; a < C::NI; a++) {

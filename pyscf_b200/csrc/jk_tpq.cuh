@@ -151,8 +151,11 @@ B2_HD void tpq_eri(const KParams& P, const ShellPair& bp, const ShellPair& kp, i
 }
 
 // digestion of one quartet held entirely by one thread (same update rules as phase_digest)
+// dij_pre: the D[ij] block of the stationary bra pair, loaded once per thread (n_dm_j == 1), else nullptr.
+// All density elements are fetched BEFORE the first reduction is issued: a load placed after a RED cannot be hoisted
+// above it (possible alias), which would serialise every (c,d) step on the load latency and re-read D[ij] each time.
 template <class C>
-B2_HD void tpq_digest(const KParams& P, const double* v, double f, int i0, int j0, int k0, int l0, double* jij)
+B2_HD void tpq_digest(const KParams& P, const double* v, double f, int i0, int j0, int k0, int l0, double* jij, const double* dij_pre)
 {
     using T = TpqCfg<C>;
     const int n = P.n;
@@ -161,27 +164,30 @@ B2_HD void tpq_digest(const KParams& P, const double* v, double f, int i0, int j
         for (int idm = 0; idm < P.n_dm_j; idm++) {
             const double* D = P.dmj + idm * n2;
             double* J = P.vj + idm * n2;
-            double jab[T::NAB];
+            double jab[T::NAB], dij[T::NAB], dkl[C::NK * C::NL], jkl[C::NK * C::NL];
             B2_UNROLL
-            for (int e = 0; e < T::NAB; e++) jab[e] = 0.0;
+            for (int e = 0; e < C::NK * C::NL; e++) dkl[e] = B2_LDG(&D[(size_t)(k0 + e % C::NK) * n + l0 + e / C::NK]);
+            B2_UNROLL
+            for (int e = 0; e < T::NAB; e++) {
+                jab[e] = 0.0;
+                dij[e] = dij_pre ? dij_pre[e] : B2_LDG(&D[(size_t)(i0 + e % C::NI) * n + j0 + e / C::NI]);
+            }
             B2_UNROLL
             for (int d = 0; d < C::NL; d++) {
                 B2_UNROLL
                 for (int c = 0; c < C::NK; c++) {
-                    double dkl = D[(size_t)(k0 + c) * n + l0 + d];
-                    double jkl = 0.0;
+                    double acc = 0.0;
                     B2_UNROLL
-                    for (int bb = 0; bb < C::NJ; bb++) {
-                        B2_UNROLL
-                        for (int a = 0; a < C::NI; a++) {
-                            double val = v[(d * C::NK + c) * T::NAB + bb * C::NI + a];
-                            jkl += val * D[(size_t)(i0 + a) * n + j0 + bb];
-                            jab[bb * C::NI + a] += val * dkl;
-                        }
+                    for (int e = 0; e < T::NAB; e++) {
+                        double val = v[(d * C::NK + c) * T::NAB + e];
+                        acc += val * dij[e];
+                        jab[e] += val * dkl[d * C::NK + c];
                     }
-                    red_add(&J[(size_t)(k0 + c) * n + l0 + d], 2.0 * f * jkl);
+                    jkl[d * C::NK + c] = acc;
                 }
             }
+            B2_UNROLL
+            for (int e = 0; e < C::NK * C::NL; e++) red_add(&J[(size_t)(k0 + e % C::NK) * n + l0 + e / C::NK], 2.0 * f * jkl[e]);
             if (P.n_dm_j == 1) {
                 B2_UNROLL
                 for (int e = 0; e < T::NAB; e++) jij[e] += 2.0 * f * jab[e];
@@ -213,11 +219,11 @@ B2_HD void tpq_digest(const KParams& P, const double* v, double f, int i0, int j
                 for (int c = 0; c < C::NK; c++) {
                     B2_UNROLL
                     for (int bb = 0; bb < C::NJ; bb++) {
-                        double djl = D[(size_t)(j0 + bb) * n + l0 + d], djk = D[(size_t)(j0 + bb) * n + k0 + c];
+                        double djl = B2_LDG(&D[(size_t)(j0 + bb) * n + l0 + d]), djk = B2_LDG(&D[(size_t)(j0 + bb) * n + k0 + c]);
                         B2_UNROLL
                         for (int a = 0; a < C::NI; a++) {
                             double val = v[(d * C::NK + c) * T::NAB + bb * C::NI + a];
-                            double dil = D[(size_t)(i0 + a) * n + l0 + d], dik = D[(size_t)(i0 + a) * n + k0 + c];
+                            double dil = B2_LDG(&D[(size_t)(i0 + a) * n + l0 + d]), dik = B2_LDG(&D[(size_t)(i0 + a) * n + k0 + c]);
                             kik[a * C::NK + c] += val * djl;
                             kil[a * C::NL + d] += val * djk;
                             kjk[bb * C::NK + c] += val * dil;
@@ -270,9 +276,13 @@ void tpq_block(const KParams& P, int bx, int by, int bz)
     unsigned long long ncomp = 0, nskip = 0;
     for (int tid = 0; tid < T::NT; tid++) {
 #endif
-        double jij[T::NAB];
+        double jij[T::NAB], dij[T::NAB];
+        const bool one_j = P.vj && P.n_dm_j == 1;
         B2_UNROLL
-        for (int e = 0; e < T::NAB; e++) jij[e] = 0.0;
+        for (int e = 0; e < T::NAB; e++) {
+            jij[e] = 0.0;
+            dij[e] = one_j ? B2_LDG(&P.dmj[(size_t)(bpair.i0 + e % C::NI) * P.n + bpair.j0 + e / C::NI]) : 0.0;
+        }
         int mine = 0, skipped = 0;
         for (int kk = kbeg + tid; kk < kend; kk += T::NT) {
             const ShellPair kp = load_pair(P.ket_pairs + kk);
@@ -288,7 +298,7 @@ void tpq_block(const KParams& P, int bx, int by, int bz)
             if (P.same_class && kk == bx) f *= 0.5;
             double v[T::NOUT];
             tpq_eri<C, SR>(P, bpair, kp, ib0, ib1, v);
-            tpq_digest<C>(P, v, f, bpair.i0, bpair.j0, kp.i0, kp.j0, jij);
+            tpq_digest<C>(P, v, f, bpair.i0, bpair.j0, kp.i0, kp.j0, jij, one_j ? dij : nullptr);
         }
 #if defined(__CUDA_ARCH__)
         // warp-reduce the stationary J[ij] block, one reduction per warp and element
