@@ -38,6 +38,7 @@ WORKLOADS = {
     'c60-def2svp-df': dict(geom='c60', basis='def2-svp', nocc=180, kind='df'),
     'benzene-def2svp-df': dict(geom='benzene', basis='def2-svp', nocc=21, kind='df'),
     'gly30-ccpvdz-df': dict(geom='gly30', basis='cc-pvdz', nocc=455, kind='df'),   # BASELINE config 5 (full-range J/K part)
+    'taxol-def2tzvp-df': dict(geom='taxol', basis='def2-tzvp', nocc=226, kind='df'),  # BASELINE config 4 (111 GB tensor: needs >= 2 GPUs)
     'gly4-ccpvdz-df': dict(geom='gly4', basis='cc-pvdz', nocc=65, kind='df'),
 }
 

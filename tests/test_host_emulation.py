@@ -30,6 +30,15 @@ def test_table_sizes_match_survey():
     assert (m.natm, m.nbas, m.nao, m.nelectron // 2) == (213, 881, 2154, 455)
     aux = make_auxmol(m)
     assert (aux.nbas, aux.nao) == (3732, 10586)
+    m = gto.M(atom=geometry('taxol'), basis='def2-tzvp')     # config 4: C47H51NO14 (tools/make_taxol.py)
+    assert (m.natm, m.nbas, m.nao, m.nelectron // 2, int(m._bas[:, 1].max())) == (113, 886, 2228, 226, 3)
+    aux = make_auxmol(m)
+    assert (aux.nbas, aux.nao, int(aux._bas[:, 1].max())) == (1856, 5598, 4)
+    # chemically sane: no two atoms closer than a bond, no non-hydrogen pair closer than 1.19 A (C=O)
+    r = m.atom_coords() * 0.52917721092
+    d = np.sqrt(((r[:, None] - r[None]) ** 2).sum(-1)) + 10 * np.eye(m.natm)
+    heavy = m._atm[:, 0] > 1
+    assert d.min() > 0.94 and d[np.ix_(heavy, heavy)].min() > 1.19
 
 
 def test_env_layout():
