@@ -169,6 +169,7 @@ def run_ours(args, rank, world):
     time.sleep(0.3)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kern_ms = []
+    stage_log = []
     launches = 0
     torch.cuda.synchronize()
     t_wall0 = time.time()
@@ -183,6 +184,8 @@ def run_ours(args, rank, world):
         st = h.stats()
         kern_ms.append(st['ms_kernels'])
         launches += st['kernel_launches']
+        if is_df:
+            stage_log.append(h.df_stage_times())
     torch.cuda.synchronize()
     t_wall = time.time() - t_wall0
     step_ms = [a.elapsed_time(b) for a, b in evs]
@@ -256,19 +259,56 @@ def run_ours(args, rank, world):
     else:
         naux = eng.get_naoaux()
         ns = eng.k_slices
+        nsl = ns * (ns + 1) // 2                                   # slice GEMMs actually executed (k + l < ns)
         fp64_flops = 4.0 * naux * nao * nao * w['nocc']           # dsymm + dgemm count of the reference
-        int8_ops = fp64_flops * ns * (ns + 1) / 2                  # slice GEMMs actually executed
+        int8_ops = fp64_flops * nsl
         bf16_peak = peaks.get('bf16_tflops_sustained', 1400.0)
-        ach = int8_ops / world / (kernel_ms * 1e-3) / 1e12
+        tensor_peak = 2 * bf16_peak
         cderi_bytes = naux * nao * (nao + 1) / 2 * 8
-        roof = {'bound': 'tensor', 'achieved': ach, 'peak': 2 * bf16_peak, 'unit': 'TOP/s (int8)', 'frac': ach / (2 * bf16_peak),
-                'traffic': None, 'kernel': 'i8gemm_ar_kernel + i8gemm_kernel (tcgen05.mma.kind::i8 slice GEMMs of DF-K)',
-                'kernel_ms_per_step': kernel_ms, 'slice_gemms': ns * (ns + 1) // 2, 'fp64_equiv_flops_per_step': fp64_flops,
-                'fp64_equiv_tflops': fp64_flops / world / (kernel_ms * 1e-3) / 1e12,
-                'peak_source': '2 x MEASURED_PEAKS.json bf16_tflops_sustained (int8 dense = 2x bf16 on sm_100a; of measured); '
-                               'kernel_ms covers the whole DF J+K build (J pass, slicing, both GEMM stages)',
-                'hbm': {'bound': 'hbm', 'note': 'DF-J: two streaming passes over cderi', 'alg_bytes_per_step': cderi_bytes,
-                        'peak': hbm_peak, 'unit': 'GB/s'}}
+        # per-stage device times of the timed steps (CUDA events around every launch, b200jk_df_stage_times)
+        stg = {k: (float(np.mean([t[k][0] for t in stage_log])), int(stage_log[0][k][1])) for k in stage_log[0]}
+        half_ops = int8_ops / 2 / world                            # each GEMM stage carries half of the 4*naux*nao^2*nocc count
+        stages = {}
+        for k in ('k_gemm1', 'k_gemm2'):
+            ms_k, n_k = stg[k]
+            if n_k:
+                stages[k] = {'kernel': 'i8gemm_ar_kernel' if k == 'k_gemm1' else 'i8gemm_kernel', 'bound': 'tensor',
+                             'launches_per_step': n_k, 'ms_per_launch': ms_k / n_k, 'ms_per_step': ms_k,
+                             'alg_int8_ops_per_launch': half_ops / n_k, 'achieved': half_ops / (ms_k * 1e-3) / 1e12,
+                             'peak': tensor_peak, 'unit': 'TOP/s (int8)', 'frac': half_ops / (ms_k * 1e-3) / 1e12 / tensor_peak}
+        for k in ('j_rho', 'j_acc'):
+            ms_k, n_k = stg[k]
+            if n_k:
+                stages[k] = {'kernel': 'dfj_rho_kernel' if k == 'j_rho' else 'dfj_acc_kernel', 'bound': 'hbm',
+                             'launches_per_step': n_k, 'ms_per_step': ms_k, 'alg_bytes_per_step': cderi_bytes / world,
+                             'achieved': cderi_bytes / world / (ms_k * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                             'frac': cderi_bytes / world / (ms_k * 1e-3) / 1e9 / hbm_peak}
+        ms_k, n_k = stg['k_slice']
+        stages['k_slice'] = {'kernel': 'rowmax_kernel + split_long_kernel (int8 slicing of Y)', 'ms_per_step': ms_k,
+                             'launches_per_step': n_k}
+        ach = int8_ops / world / (kernel_ms * 1e-3) / 1e12
+        g1 = stages.get('k_gemm1')
+        if g1:     # the dominant kernel: stage 1 of DF-K
+            roof = {'bound': 'tensor', 'achieved': g1['achieved'], 'peak': tensor_peak, 'unit': 'TOP/s (int8)', 'frac': g1['frac'],
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one i8gemm_ar launch of this workload, ncu --set full
+                    # (profiles/r01_ncu_i8ar.txt); null for other workloads
+                    'traffic': 2.018729e9 + 446.094080e6 if (args.workload == 'c60-def2svp-df' and world == 1) else None,
+                    'kernel': 'i8gemm_ar_kernel (tcgen05.mma.kind::i8, stage 1 of DF-K: Y = (P|mu nu) C~), CUDA events around '
+                              'each of its launches inside the timed steps',
+                    'ms_per_launch': g1['ms_per_launch'], 'launches_per_step': g1['launches_per_step'],
+                    'alg_int8_ops_per_launch': g1['alg_int8_ops_per_launch']}
+        else:      # cuBLAS DGEMM yardstick engine or general-density path: whole build only
+            roof = {'bound': 'tensor', 'achieved': ach, 'peak': tensor_peak, 'unit': 'TOP/s (int8)', 'frac': ach / tensor_peak,
+                    'traffic': None, 'kernel': 'whole DF J+K build'}
+        roof.update({
+                'slice_gemms': nsl, 'stages': stages,
+                'whole_build': {'ms_per_step': kernel_ms, 'achieved': ach, 'frac': ach / tensor_peak, 'unit': 'TOP/s (int8)',
+                                'note': 'all int8 slice-GEMM work over the whole DF J+K build time (J passes, slicing, both GEMM stages)',
+                                'fp64_equiv_flops_per_step': fp64_flops,
+                                'fp64_equiv_tflops': fp64_flops / world / (kernel_ms * 1e-3) / 1e12},
+                'peak_source': 'tensor: 2 x MEASURED_PEAKS.json bf16_tflops_sustained (int8 dense = 2x bf16 on sm_100a; sustained '
+                               'because the kernel runs inside a long step); hbm: MEASURED_PEAKS.json hbm_gbs'
+                               if peaks else 'fallback 2 x 1400 TFLOP/s, 6650 GB/s (B200_PROFILING.md)'})
         path = 'DF J/K (cderi resident, K via tcgen05 int8 slices, %d slices)' % ns
     # ---- CPU baseline (oracle port), rank 0, N=1 only
     cpu = None

@@ -86,6 +86,16 @@ int b200jk_df_jk_device(b200jk_handle h, const double* dm_dev, int n_dm, int nao
 /* K-build engine for the occupied-orbital path: mode 1 (default) = tcgen05 int8-slice GEMMs (i8gemm.cuh) with
  * `nslices` 7-bit slices (7 -> ~1e-11 relative), mode 0 = cuBLAS DGEMM on the FP64 pipe (kept as yardstick). */
 int b200jk_df_set_kmode(b200jk_handle h, int mode, int nslices);
+/* Device time of the stages of the last b200jk_df_jk[_device] call, from CUDA events recorded around every launch on
+ * the launching stream (no reference equivalent; the reference brackets the whole loop with logger.timer 'vj and vk',
+ * pyscf/df/df_jk.py:412): ms[s] = summed milliseconds, count[s] = launches of stage s; n <= B200JK_DF_NSTAGE entries. */
+enum { B200JK_DF_STAGE_J_RHO = 0,    /* rho_P = sum cderi[P,:] dmtril           (streams the tensor once) */
+       B200JK_DF_STAGE_J_ACC = 1,    /* J~ = sum_P rho_P cderi[P,:]             (streams it a second time) */
+       B200JK_DF_STAGE_K_GEMM1 = 2,  /* Y = (P|mu nu) C~     tcgen05 i8gemm_ar_kernel */
+       B200JK_DF_STAGE_K_SLICE = 3,  /* int8 slicing of Y */
+       B200JK_DF_STAGE_K_GEMM2 = 4,  /* K += Y Y^T           tcgen05 i8gemm_kernel */
+       B200JK_DF_NSTAGE = 5 };
+int b200jk_df_stage_times(b200jk_handle h, double* ms, int* count, int n);
 /* Rows of the tensor held by this handle: [row0, row0+nrow) of the naux rows.  The whole tensor unless
  * b200jk_set_shard(rank, world) was called BEFORE b200jk_df_build, in which case only this rank's rows are built
  * (the 3-center integrals are computed in bounded batches of AO shell pairs and multiplied by this rank's rows of L^-1). */

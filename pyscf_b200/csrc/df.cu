@@ -68,7 +68,10 @@ struct DFState {
     cusolverDnHandle_t cusolver = nullptr;
     i8g::SliceStack SA, SC, SY;
     bool sa_persistent = false; int sa_ns = 0, sa_lo = 0, sa_hi = 0;   // slices of the whole unpacked tensor kept resident (memory permitting)
+    // per-stage device timers of the last b200jk_df_jk call (CUDA events on the launching stream, read after the final sync)
+    std::vector<cudaEvent_t> tm_ev; std::vector<int> tm_tag; size_t tm_used = 0;
 #endif
+    double stage_ms[B200JK_DF_NSTAGE] = {0}; int stage_n[B200JK_DF_NSTAGE] = {0};
 };
 
 namespace {
@@ -76,6 +79,9 @@ namespace {
 void df_free(DFState* d)
 {
     if (!d) return;
+#ifndef B200JK_EMULATE
+    for (cudaEvent_t e : d->tm_ev) cudaEventDestroy(e);
+#endif
     dev_free(d->d_aprims);
     for (int l = 0; l <= LMAX; l++) { dev_free(d->d_akets[l]); dev_free(d->d_aket_off[l]); }
     dev_free(d->d_acart_sh); dev_free(d->d_acart_comp); dev_free(d->d_asph_sh); dev_free(d->d_asph_m);
@@ -809,6 +815,15 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
         uint64_t launches = 0;
 #ifndef B200JK_EMULATE
         CK(cudaEventRecord(h->ev0, st));
+        d->tm_used = 0; d->tm_tag.clear();
+        // mark(tag) ... mark(-1) brackets one stage on the stream; no host synchronisation
+        auto mark = [&](int tag) {
+            if (d->tm_used == d->tm_ev.size()) { cudaEvent_t e; CK(cudaEventCreate(&e)); d->tm_ev.push_back(e); }
+            CK(cudaEventRecord(d->tm_ev[d->tm_used++], st));
+            d->tm_tag.push_back(tag);
+        };
+#else
+        auto mark = [&](int) {};
 #endif
         if (vj) {
             DmTrilFn tf{d->d_dm, d->d_dmtril, nao, npair};
@@ -820,13 +835,16 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
             const unsigned nseg = (unsigned)((npair + seglen - 1) / seglen);
             // two streaming passes over the tensor (rho, then J): 2 launches, both HBM-bound
             (void)rb;
+            mark(B200JK_DF_STAGE_J_RHO);
             for (int r0 = r_lo; r0 < r_hi; r0 += 32768) {
                 int nr = std::min(32768, r_hi - r0);
                 dfj_rho_kernel<<<dim3(nseg, nr, n_dm), 256, 0, st>>>(d->d_cderi, d->d_dmtril, d->d_rho, npair, r0, naux, seglen);
                 launches++;
             }
+            mark(B200JK_DF_STAGE_J_ACC);
             dfj_acc_kernel<<<(unsigned)((npair + 255) / 256), 256, 0, st>>>(d->d_cderi, d->d_rho, d->d_vjtril, npair, r_lo, r_hi - r_lo, naux, n_dm);
             launches++;
+            mark(-1);
             CK(cudaGetLastError());
 #else
             for (int s = 0; s < n_dm; s++)
@@ -930,11 +948,15 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
                         };
                         tick(-1);
                         tick(0);
+                        mark(B200JK_DF_STAGE_K_GEMM1);
                         i8g::gemm_ar(d->SA, d->sa_persistent ? (r0 - r_lo) * nao : 0, nr * nao, d->SC, d->d_Y2, (long)nr * nocc, nao, st);
                         tick(1);
+                        mark(B200JK_DF_STAGE_K_SLICE);
                         i8g::split_rows(d->SY, d->d_Y2, (long)nr * nocc, nao, nr * nocc, d->k_slices, st);
                         tick(2);
+                        mark(B200JK_DF_STAGE_K_GEMM2);
                         i8g::gemm(d->SY, d->SY, d->d_vk + (size_t)s * n2, nao, 0, true, st);
+                        mark(-1);
                         tick(3);
                         if (prof && r0 + kb >= r_hi) {
                             fprintf(stderr, "[df-k profile] zeroY2 %.2f ms, gemm1 %.2f ms, splitY %.2f ms, gemm2 %.2f ms (sum over blocks, kb=%d)\n",
@@ -999,6 +1021,14 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         h->stats.ms_kernels = ms;
+        for (int i = 0; i < B200JK_DF_NSTAGE; i++) { d->stage_ms[i] = 0; d->stage_n[i] = 0; }
+        for (size_t i = 0; i + 1 < d->tm_used; i++) {
+            int tag = d->tm_tag[i];
+            if (tag < 0) continue;
+            float t = 0;
+            CK(cudaEventElapsedTime(&t, d->tm_ev[i], d->tm_ev[i + 1]));
+            d->stage_ms[tag] += t; d->stage_n[tag]++;
+        }
 #endif
         auto t1 = std::chrono::steady_clock::now();
         h->stats.ms_total = std::chrono::duration<double, std::milli>(t1 - t0).count();
@@ -1017,6 +1047,16 @@ extern "C" int b200jk_df_jk_device(b200jk_handle h, const double* dm, int n_dm, 
                                    double* vj, double* vk)
 {
     return df_jk_impl(h, dm, n_dm, nao, occ, nocc, hermi, vj, vk, true);
+}
+
+extern "C" int b200jk_df_stage_times(b200jk_handle h, double* ms, int* count, int n)
+{
+    if (!h || !h->df || !ms || !count) { set_err(h, "call b200jk_df_build first"); return 1; }
+    for (int i = 0; i < n; i++) {
+        ms[i] = i < B200JK_DF_NSTAGE ? h->df->stage_ms[i] : 0.0;
+        count[i] = i < B200JK_DF_NSTAGE ? h->df->stage_n[i] : 0;
+    }
+    return 0;
 }
 
 extern "C" int b200jk_df_set_kmode(b200jk_handle h, int mode, int nslices)

@@ -193,6 +193,10 @@ class DF:
     def stats(self):
         return self._handle.stats()
 
+    def stage_times(self):
+        """Device time per stage of the last get_jk: {'j_rho' | 'j_acc' | 'k_gemm1' | 'k_slice' | 'k_gemm2': (ms, launches)}."""
+        return self._handle.df_stage_times()
+
 
 class TaggedDM(np.ndarray):
     """ndarray carrying mo_coeff / mo_occ like lib.tag_array (pyscf/lib/numpy_helper.py; hf.py:868)."""

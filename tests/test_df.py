@@ -135,6 +135,14 @@ def test_df_gpu_benzene_properties():
     from pyscf_b200.jk import VHFOpt
     ej, ek = VHFOpt(mol).get_jk(a)
     assert abs(ja - ej).max() < 0.1 and abs(ka - ek).max() < 0.1   # fitting error of def2-svp-jkfit, elements O(100)
+    # stage timers of the tensor-core K path (orbital-tagged density): every stage ran and was timed on the device
+    c, _ = np.linalg.qr(rng.standard_normal((nao, 21)))
+    from pyscf_b200.df import TaggedDM
+    vj, vk = d.get_jk(TaggedDM(2 * c.dot(c.T), mo_coeff=c, mo_occ=np.full(21, 2.0)))
+    st = d.stage_times()
+    assert all(st[k][1] >= 1 and st[k][0] > 0 for k in ('j_rho', 'j_acc', 'k_gemm1', 'k_slice', 'k_gemm2')), st
+    assert sum(v[0] for v in st.values()) <= d.stats()['ms_kernels'] * 1.05
+    assert abs(vk - d.get_jk(2 * c.dot(c.T))[1]).max() < 1e-9      # tcgen05 slices == FP64 general-density path
 
 
 @pytest.mark.gpu
