@@ -11,9 +11,13 @@ Timed numbers
                         stream), CUDA events per step, 256 MiB L2 flush between steps outside the event pairs.
   e2e                 : the same build through the public plugin call VHFOpt.get_jk with pinned HOST buffers
                         (H2D of D and D2H of J,K inside the timed region).
-  roofline            : the class kernels (one template, 55 instantiations) against the measured FP64
+  roofline            : direct: the class kernels (one template, 55 instantiations) against the measured FP64
                         FMA-pipe peak (b200jk_fp64_peak micro-benchmark; the 4-center path is FP64-bound,
                         SURVEY.md §8d) and, beside it, the HBM figure (algorithmic bytes / time).
+                        DF: the dominant kernel (i8gemm_ar_kernel, stage 1 of DF-K) per launch, from CUDA events the
+                        library records around every launch of the timed steps (b200jk_df_stage_times), against
+                        2 x the measured bf16 tensor peak; the other stages (stage 2, slicing, the two HBM-bound DF-J
+                        passes) and the whole-build figure are listed under roofline.stages / roofline.whole_build.
   cpu_baseline        : the CPU oracle (McMurchie-Davidson port of the reference path, OpenMP, all host cores)
                         on the same workload; rank 0, N=1 only.
 --impl reference times that CPU arm alone with the same JSON schema.

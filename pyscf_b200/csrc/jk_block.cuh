@@ -14,6 +14,9 @@
 namespace b200jk {
 
 constexpr int KCH_MAX = 512;  // ket pairs examined per CTA
+#ifndef B2_CTA_THREADS
+#define B2_CTA_THREADS 192   // target CTA size of the block kernels (tuning knob)
+#endif
 
 struct KParams {
     const ShellPair* bra_pairs; int nbra;
@@ -41,7 +44,7 @@ struct GroupCfg {
     static constexpr int GW = (GP + 31) / 32;                                // warps per group
     static constexpr int TG = GW * 32;                                       // threads per group
     static constexpr int QPG = GP <= 32 ? 32 / GP : 1;                       // quartets in flight per group
-    static constexpr int NG0 = 192 / TG;
+    static constexpr int NG0 = B2_CTA_THREADS / TG;
     static constexpr int NG1 = NG0 < 1 ? 1 : (NG0 > 8 ? 8 : NG0);
     static constexpr int NG = (NG1 * QPG > 64) ? ((64 / QPG) < 1 ? 1 : 64 / QPG) : NG1;   // groups per CTA, <= 64 quartet slots
     static constexpr int NT = NG * TG;

@@ -9,6 +9,17 @@ namespace b200jk {
 // lanes doing useful work when a quartet needs g threads (sub-warp packing or whole warps)
 constexpr int lane_eff_permille(int g) { return g <= 32 ? (32 / g) * g * 1000 / 32 : g * 1000 / (((g + 31) / 32) * 32); }
 
+// compile-time tuning knobs (tools/build_variant.sh builds A/B libraries with other values)
+#ifndef B2_NVMAX
+#define B2_NVMAX 30        // largest register block (doubles) of ERI accumulators per thread
+#endif
+#ifndef B2_WANT_CTAS
+#define B2_WANT_CTAS 8     // CTAs per SM a class launch aims for when it sizes the ket chunks
+#endif
+#ifndef B2_CARVEOUT
+#define B2_CARVEOUT 50     // shared-memory share of the 228 KB L1/shared array requested for the block kernels (percent)
+#endif
+
 // number of bra-component parts per quartet: register block between 15 and 40 doubles (thread-local
 // horizontal recurrences are amortised over the block), then maximise lane use
 constexpr int choose_np(int ni, int nj, int nkl)
@@ -16,7 +27,7 @@ constexpr int choose_np(int ni, int nj, int nkl)
     int nab = ni * nj;
     int best = 0, best_eff = -1;
     for (int np = 1; np <= nj; np++) {
-        if (nj % np != 0 || nab / np > 30) continue;
+        if (nj % np != 0 || nab / np > B2_NVMAX) continue;
         if (best && nab / np < 15) break;
         if (nkl * np > 512) break;
         int eff = lane_eff_permille(nkl * np);
@@ -29,7 +40,7 @@ constexpr int choose_np(int ni, int nj, int nkl)
 // the class fills the 148 SMs several times over
 inline int pick_kchunk(int nbra, int nket, int unit, int cap)
 {
-    long want_ctas = 148L * 8;
+    long want_ctas = 148L * B2_WANT_CTAS;
     long ny = (want_ctas + nbra - 1) / nbra;
     long kc = (nket + ny - 1) / ny;
     if (kc < unit) kc = unit;
@@ -55,8 +66,11 @@ __global__ void __launch_bounds__(TpqCfg<C>::NT) jk_tpq_kernel(const KParams P)
     const int bx = blockIdx.x * P.shard_world + P.shard_rank;
     if (bx < P.nbra) tpq_block<C, SR>(P, bx, blockIdx.y, blockIdx.z);
 }
+#ifndef B2_MINB
+#define B2_MINB 1   // resident CTAs per SM the register allocator must leave room for (tuning knob)
+#endif
 template <class C, bool SR>
-__global__ void __launch_bounds__(GroupCfg<C>::NT) jk_class_kernel(const KParams P)
+__global__ void __launch_bounds__(GroupCfg<C>::NT, B2_MINB) jk_class_kernel(const KParams P)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     BlockSmem<C>& sm = *reinterpret_cast<BlockSmem<C>*>(smraw);
@@ -80,7 +94,7 @@ void launch_block_kernel(const KParams& P, dim3 grid, int nt, size_t smem, b2_st
         cudaError_t e = cudaFuncSetAttribute(jk_class_kernel<C, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
         // leave half of the 228 KB for L1 (Rys tables, density blocks); the other half lets several CTAs co-reside
-        cudaFuncSetAttribute(jk_class_kernel<C, SR>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+        cudaFuncSetAttribute(jk_class_kernel<C, SR>, cudaFuncAttributePreferredSharedMemoryCarveout, B2_CARVEOUT);
         configured = true;
     }
     jk_class_kernel<C, SR><<<grid, nt, smem, st>>>(P);

@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""A/B timing of direct-J/K library variants (tools/build_variant.sh) on one workload: for every library given, the
+device time of a full build (library CUDA events, concurrent class streams, best and mean of N) and the max deviation of
+J,K from the first library's result.  usage: python tools/ab_direct.py [--geom benzene --basis cc-pvtz] lib1.so lib2.so ..."""
+import argparse, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+from pyscf_b200 import gto
+from pyscf_b200.gto.mole import geometry
+from pyscf_b200.jk import VHFOpt
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--geom', default='benzene')
+ap.add_argument('--basis', default='cc-pvtz')
+ap.add_argument('--nocc', type=int, default=21)
+ap.add_argument('--n', type=int, default=10)
+ap.add_argument('libs', nargs='+')
+a = ap.parse_args()
+mol = gto.M(atom=geometry(a.geom), basis=a.basis)
+c, _ = np.linalg.qr(np.random.RandomState(1).standard_normal((mol.nao, a.nocc)))
+dm = 2 * c.dot(c.T)
+ref = None
+out = {}
+for path in a.libs:
+    name = os.path.basename(path)
+    try:
+        opt = VHFOpt(mol, libpath=os.path.abspath(path))
+        for _ in range(3):
+            vj, vk = opt.get_jk(dm)
+        ms = []
+        for _ in range(a.n):
+            vj, vk = opt.get_jk(dm)
+            ms.append(opt.stats()['ms_kernels'])
+        if ref is None:
+            ref = (vj, vk)
+        err = max(abs(vj - ref[0]).max(), abs(vk - ref[1]).max())
+        out[name] = {'best_ms': min(ms), 'mean_ms': float(np.mean(ms)), 'max_abs_dev_vs_first': float(err)}
+        print('%-28s best %8.3f ms  mean %8.3f ms  |dJK| vs first %.1e' % (name, min(ms), np.mean(ms), err), flush=True)
+        opt.close()
+    except Exception as e:   # a variant that fails to launch must not hide the others
+        print('%-28s FAILED: %s' % (name, e), flush=True)
+        out[name] = {'error': str(e)}
+os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'ab_direct_%s_%s.json' % (a.geom, a.basis)), 'w'), indent=1)
