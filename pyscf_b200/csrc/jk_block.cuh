@@ -17,6 +17,9 @@ constexpr int KCH_MAX = 512;  // ket pairs examined per CTA
 #ifndef B2_CTA_THREADS
 #define B2_CTA_THREADS 192   // target CTA size of the block kernels (tuning knob)
 #endif
+#ifndef B2_SMEM_CAP
+#define B2_SMEM_CAP 0        // if > 0: fewer groups per CTA so that the quartet slots of a CTA stay below this many bytes
+#endif                       // (several small CTAs per SM instead of one that owns all of its shared memory)
 
 struct KParams {
     const ShellPair* bra_pairs; int nbra;
@@ -46,7 +49,9 @@ struct GroupCfg {
     static constexpr int QPG = GP <= 32 ? 32 / GP : 1;                       // quartets in flight per group
     static constexpr int NG0 = B2_CTA_THREADS / TG;
     static constexpr int NG1 = NG0 < 1 ? 1 : (NG0 > 8 ? 8 : NG0);
-    static constexpr int NG = (NG1 * QPG > 64) ? ((64 / QPG) < 1 ? 1 : 64 / QPG) : NG1;   // groups per CTA, <= 64 quartet slots
+    static constexpr int NG2 = (NG1 * QPG > 64) ? ((64 / QPG) < 1 ? 1 : 64 / QPG) : NG1;  // groups per CTA, <= 64 quartet slots
+    static constexpr int NGC = B2_SMEM_CAP > 0 ? (int)(B2_SMEM_CAP / (QPG * sizeof(SlotSmem<C>))) : NG2;
+    static constexpr int NG = NGC < 1 ? 1 : (NGC < NG2 ? NGC : NG2);
     static constexpr int NT = NG * TG;
     static constexpr int NSLOT = NG * QPG;
 };
@@ -161,6 +166,7 @@ void group_proc(const KParams& P, BlockSmem<C>& sm, int grp, int nk, int bx,
                         const ShellPair& kp = P.ket_pairs[kk];
                         s.kl = kk; s.k0 = kp.i0; s.l0 = kp.j0;
                         s.nprim_k = kp.nprim; s.prim_off_k = kp.prim_off;
+                        s.nq = nbp * kp.nprim * (SR ? 2 : 1);
                         double f = 1.0;
                         if (sm.bra.same) f *= 0.5;
                         if (kp.same) f *= 0.5;
@@ -173,7 +179,7 @@ void group_proc(const KParams& P, BlockSmem<C>& sm, int grp, int nk, int bx,
                         for (int e2 = 0; e2 < kp.nprim; e2++) s.kprim[e2] = P.prims[kp.prim_off + e2];
 #endif
                     } else {
-                        s.nprim_k = 0;
+                        s.nprim_k = 0; s.nq = 0;
                     }
                 }
                 B2_UNROLL
@@ -185,13 +191,71 @@ void group_proc(const KParams& P, BlockSmem<C>& sm, int grp, int nk, int bx,
 #if defined(__CUDA_ARCH__)
         if (ctx.valid && sm.slot[ctx.slot].active) { bulk_wait(&sm.mbar_slot[ctx.slot], ctx.kpar); ctx.kpar ^= 1; }
 #endif
+        constexpr bool sr_op = SR;   // erfc = Coulomb - erf: every primitive quartet is visited twice (omega < 0)
+        if constexpr (C::PB > 1) {
+            // ---- primitive batching: PB primitive quartets per round.  Quartet e of the slot (e < nq) is
+            //      (bra primitive ibp, ket primitive ikp, pass sr) with e = (ibp * nprim_k + ikp) * passes + sr,
+            //      the same order as the one-at-a-time loop below, so the sums are bit-identical.
+            int nqmax = 0;
+            for (int q = 0; q < GC::QPG; q++) {
+                int n_ = sm.slot[grp * GC::QPG + q].nq;
+                nqmax = n_ > nqmax ? n_ : nqmax;
+            }
+            for (int e0 = 0; e0 < nqmax; e0 += C::PB) {
+                // phase A: PB*NR root tasks over the G lanes of each quartet
+                B2_GROUP_LANES(lt)
+                    LaneCtx<C>& L = B2_CTX(tid0 + lt);
+                    if (L.valid) {
+                        SlotSmem<C>& s = sm.slot[L.slot];
+                        const int nq = s.nq, nkp = s.nprim_k;
+                        for (int task = L.t.g; task < C::PB * C::NR; task += C::G) {
+                            const int b = task / C::NR, r = task - b * C::NR;
+                            const int e = e0 + b;
+                            if (e < nq) {
+                                const int sr = sr_op ? (e & 1) : 0;
+                                const int pq = sr_op ? (e >> 1) : e;
+                                const int ibp = pq / nkp, ikp = pq - ibp * nkp;
+                                phase_root_one<C>(s, b, r, sm.bprim[ibp], s.kprim[ikp], P.tb,
+                                                  sr_op ? (sr ? -P.omega : 0.0) : P.omega, (sr_op && sr) ? -1.0 : 1.0);
+                            }
+                        }
+                    }
+                B2_END
+                group_sync<C>(grp);
+                // phase B: PB*3*NR (quartet, root, direction) recurrence tasks
+                B2_GROUP_LANES(lt)
+                    LaneCtx<C>& L = B2_CTX(tid0 + lt);
+                    if (L.valid) {
+                        SlotSmem<C>& s = sm.slot[L.slot];
+                        const int nq = s.nq;
+                        for (int task = L.t.g; task < C::PB * 3 * C::NR; task += C::G) {
+                            const int b = task / (3 * C::NR), rem = task - b * (3 * C::NR);
+                            const int r = rem / 3, x = rem - 3 * r;
+                            if (e0 + b < nq) vrr_one<C>(s, b, r, x);
+                        }
+                    }
+                B2_END
+                group_sync<C>(grp);
+                // phase D: every lane sums the batch into its register block
+                B2_GROUP_LANES(lt)
+                    LaneCtx<C>& L = B2_CTX(tid0 + lt);
+                    if (L.valid) {
+                        SlotSmem<C>& s = sm.slot[L.slot];
+                        const int nq = s.nq;
+                        for (int b = 0; b < C::PB; b++)
+                            if (e0 + b < nq) phase_accumulate<C>(s, L.t, sm.bra.ABx, sm.bra.ABy, sm.bra.ABz, b);
+                    }
+                B2_END
+                // the next round's phase A rewrites U/W/pc, which phase B of this round (already behind a barrier) read;
+                // H is rewritten only after the barrier that follows phase A
+            }
+        } else {
         int npmax = 0;
         for (int q = 0; q < GC::QPG; q++) {
             int nk_ = sm.slot[grp * GC::QPG + q].nprim_k;
             npmax = nk_ > npmax ? nk_ : npmax;
         }
         npmax *= nbp;
-        constexpr bool sr_op = SR;   // erfc = Coulomb - erf: every primitive quartet is visited twice (omega < 0)
         if (sr_op) npmax *= 2;
 
         for (int ip = 0; ip < npmax; ip++) {
@@ -227,6 +291,7 @@ void group_proc(const KParams& P, BlockSmem<C>& sm, int grp, int nk, int bx,
                     }
                 }
             B2_END
+        }
         }
         // ---- phase E: digestion
         B2_GROUP_LANES(lt)

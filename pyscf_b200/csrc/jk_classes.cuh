@@ -16,6 +16,9 @@ constexpr int lane_eff_permille(int g) { return g <= 32 ? (32 / g) * g * 1000 / 
 #ifndef B2_WANT_CTAS
 #define B2_WANT_CTAS 8     // CTAs per SM a class launch aims for when it sizes the ket chunks
 #endif
+#ifndef B2_PBMAX
+#define B2_PBMAX 1         // largest primitive batch (QClass::PB) of the block kernels; 1 = one primitive quartet per round
+#endif
 #ifndef B2_CARVEOUT
 #define B2_CARVEOUT 50     // shared-memory share of the 228 KB L1/shared array requested for the block kernels (percent)
 #endif
@@ -36,6 +39,16 @@ constexpr int choose_np(int ni, int nj, int nkl)
     return best ? best : nj;
 }
 
+// primitive quartets per phase round (QClass::PB): double while the (root, direction) tasks of the batch still fit in
+// ONE round over the lanes reserved for a quartet and the 2-D integral buffers of a CTA stay below 64 KB
+constexpr int choose_pb(int g, int nr, int h_bytes, int nslot)
+{
+    int gp = g <= 32 ? g : ((g + 31) / 32) * 32;
+    int pb = 1;
+    while (2 * pb <= B2_PBMAX && 2 * pb * 3 * nr <= gp && 2 * pb * h_bytes * nslot <= 64 * 1024) pb *= 2;
+    return pb;
+}
+
 // kets per CTA: at least one batch (`unit` kets in flight per CTA), at most `cap`, and small enough that
 // the class fills the 148 SMs several times over
 inline int pick_kchunk(int nbra, int nket, int unit, int cap)
@@ -51,7 +64,9 @@ inline int pick_kchunk(int nbra, int nket, int unit, int cap)
 template <int LI, int LJ, int LK, int LL>
 struct ClassCfg {
     static constexpr int NP = choose_np(ncart(LI), ncart(LJ), ncart(LK) * ncart(LL));
-    using C = QClass<LI, LJ, LK, LL, NP>;
+    using C1 = QClass<LI, LJ, LK, LL, NP>;
+    static constexpr int PB = choose_pb(C1::G, C1::NR, 3 * C1::NR * C1::HSP * 8, GroupCfg<C1>::NSLOT);
+    using C = QClass<LI, LJ, LK, LL, NP, PB>;
     using GC = GroupCfg<C>;
     static constexpr int NT = GC::NT;
     // kets examined per CTA: enough batches per group to amortise the prologue and the J[ij] flush

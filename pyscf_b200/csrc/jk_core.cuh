@@ -158,9 +158,12 @@ B2_HD ShellPair load_pair(const ShellPair* p)
 constexpr int MAX_PRIM_PER_PAIR = 16;   // pair lists are split so that no entry carries more primitive pairs (b200jk.cu)
 
 // ---------------------------------------------------------------------------------------------
-template <int LI_, int LJ_, int LK_, int LL_, int NP_>
+// PB_: primitive quartets processed per phase round by the block kernels (primitive batching): the Rys roots and the
+// vertical recurrences of PB_ primitive quartets are spread over the lanes of a group TOGETHER, so that groups with many
+// lanes (high angular momentum kets) are not idle while a handful of (root, direction) tasks run.  1 = one at a time.
+template <int LI_, int LJ_, int LK_, int LL_, int NP_, int PB_ = 1>
 struct QClass {
-    static constexpr int LI = LI_, LJ = LJ_, LK = LK_, LL = LL_, NP = NP_;
+    static constexpr int LI = LI_, LJ = LJ_, LK = LK_, LL = LL_, NP = NP_, PB = PB_;
     static constexpr int NI = ncart(LI), NJ = ncart(LJ), NK = ncart(LK), NL = ncart(LL);
     static_assert(NJ % NP == 0, "NP must divide the number of j components");
     static constexpr int NJP = NJ / NP;
@@ -180,13 +183,14 @@ template <class C>
 struct alignas(16) SlotSmem {
     // 2-D integrals after the vertical recurrence AND the ket transfer (k -> l), ready for per-thread bra transfer:
     // H[dir][root][(l*(LK+1)+k)*NB1P + n]; z carries weight*prefactor.  Rows of n are contiguous (LDS.128).
-    double H[3][C::NR][C::HSP];
+    // The leading index is the primitive quartet of the current batch (C::PB of them, see QClass).
+    double H[C::PB][3][C::NR][C::HSP];
     PrimPair kprim[MAX_PRIM_PER_PAIR];   // this ket's primitive pairs, staged by one bulk async copy (TMA, UBLKCP) per batch
-    double U[C::NR], W[C::NR];
-    double pc[14];               // p, q, PA[3], QC[3], PQ[3], 1/(p+q), 0.5/p, 0.5/q
+    double U[C::PB][C::NR], W[C::PB][C::NR];
+    double pc[C::PB][14];        // p, q, PA[3], QC[3], PQ[3], 1/(p+q), 0.5/p, 0.5/q
     double ccd[3][C::LL + 1][C::LL + 1];  // binom(l,t) CD^(l-t)
     double fac;                  // symmetry factor (1, 1/2, 1/4, 1/8)
-    int32_t kl, k0, l0, nprim_k, prim_off_k, active, pact, pad;
+    int32_t kl, k0, l0, nprim_k, prim_off_k, active, pact, nq;   // nq: primitive quartets of this (bra, ket) (batched path)
 };
 
 struct BraInfo {
@@ -256,16 +260,52 @@ B2_HD void phase_roots(SlotSmem<C>& s, int g, const PrimPair& bp, const PrimPair
     for (int r = g; r < C::NR; r += C::G) {
         double u, w;
         rys_root(tb, C::NR, r, x, u, w);
-        s.U[r] = u * theta;
-        s.W[r] = w * pref;
+        s.U[0][r] = u * theta;
+        s.W[0][r] = w * pref;
     }
     if (g == 0) {
-        s.pc[0] = p; s.pc[1] = q;
-        s.pc[2] = bp.PAx; s.pc[3] = bp.PAy; s.pc[4] = bp.PAz;
-        s.pc[5] = kp.PAx; s.pc[6] = kp.PAy; s.pc[7] = kp.PAz;
-        s.pc[8] = PQx; s.pc[9] = PQy; s.pc[10] = PQz;
-        s.pc[11] = ipq;
-        s.pc[12] = 0.5 / p; s.pc[13] = 0.5 / q;
+        double* pc = s.pc[0];
+        pc[0] = p; pc[1] = q;
+        pc[2] = bp.PAx; pc[3] = bp.PAy; pc[4] = bp.PAz;
+        pc[5] = kp.PAx; pc[6] = kp.PAy; pc[7] = kp.PAz;
+        pc[8] = PQx; pc[9] = PQy; pc[10] = PQz;
+        pc[11] = ipq;
+        pc[12] = 0.5 / p; pc[13] = 0.5 / q;
+    }
+}
+
+// Phase A, batched path: ONE task = root r of primitive quartet b of the batch (the caller spreads the PB*NR tasks over
+// the lanes of the group).  The task of root 0 also leaves the pair constants of its primitive quartet.
+template <class C>
+B2_HD void phase_root_one(SlotSmem<C>& s, int b, int r, const PrimPair& bp, const PrimPair& kp, const RysTables& tb, double omega,
+                          double wsign)
+{
+    double p = bp.p, q = kp.p;
+    double PQx = bp.Px - kp.Px, PQy = bp.Py - kp.Py, PQz = bp.Pz - kp.Pz;
+    double pq = p + q;
+    double rs = rsqrt(pq);
+    double ipq = rs * rs;
+    double rho = p * q * ipq;
+    double x = rho * (PQx * PQx + PQy * PQy + PQz * PQz);
+    double pref = bp.cc * kp.cc * rs * wsign;
+    double theta = 1.0;
+    if (omega > 0.0) {
+        theta = omega * omega / (omega * omega + rho);
+        x *= theta;
+        pref *= sqrt(theta);
+    }
+    double u, w;
+    rys_root(tb, C::NR, r, x, u, w);
+    s.U[b][r] = u * theta;
+    s.W[b][r] = w * pref;
+    if (r == 0) {
+        double* pc = s.pc[b];
+        pc[0] = p; pc[1] = q;
+        pc[2] = bp.PAx; pc[3] = bp.PAy; pc[4] = bp.PAz;
+        pc[5] = kp.PAx; pc[6] = kp.PAy; pc[7] = kp.PAz;
+        pc[8] = PQx; pc[9] = PQy; pc[10] = PQz;
+        pc[11] = ipq;
+        pc[12] = 0.5 / p; pc[13] = 0.5 / q;
     }
 }
 
@@ -273,21 +313,21 @@ B2_HD void phase_roots(SlotSmem<C>& s, int g, const PrimPair& bp, const PrimPair
 //   H(n; k,l) = sum_t binom(l,t) CD^(l-t) I(n, k+t)
 // so that phase D only loads one contiguous row of n per direction.
 template <class C>
-B2_HD void phase_vrr(SlotSmem<C>& s, int g)
+B2_HD void vrr_one(SlotSmem<C>& s, int b, int r, int x)
 {
-    double p = s.pc[0], q = s.pc[1];
-    double ipq = s.pc[11];
-    double hip = s.pc[12], hiq = s.pc[13];
-    for (int task = g; task < 3 * C::NR; task += C::G) {
-        int r = task / 3, x = task - 3 * r;
-        double u = s.U[r];
+    const double* pc = s.pc[b];
+    double p = pc[0], q = pc[1];
+    double ipq = pc[11];
+    double hip = pc[12], hiq = pc[13];
+    {
+        double u = s.U[b][r];
         double b00 = 0.5 * u * ipq;
         double b10 = (1.0 - u * q * ipq) * hip;
         double b01 = (1.0 - u * p * ipq) * hiq;
-        double c00 = s.pc[2 + x] - u * q * ipq * s.pc[8 + x];
-        double c0p = s.pc[5 + x] + u * p * ipq * s.pc[8 + x];
+        double c00 = pc[2 + x] - u * q * ipq * pc[8 + x];
+        double c0p = pc[5 + x] + u * p * ipq * pc[8 + x];
         double I[C::NB1][C::NT1];
-        double i0 = (x == 2) ? s.W[r] : 1.0;
+        double i0 = (x == 2) ? s.W[b][r] : 1.0;
         I[0][0] = i0;
         if (C::LB > 0) {
             I[1][0] = c00 * i0;
@@ -304,7 +344,7 @@ B2_HD void phase_vrr(SlotSmem<C>& s, int g)
                 I[n][m + 1] = val;
             }
         }
-        double* H = s.H[x][r];
+        double* H = s.H[b][x][r];
         B2_UNROLL
         for (int l = 0; l <= C::LL; l++) {
             double cf[C::LL + 1];
@@ -321,6 +361,15 @@ B2_HD void phase_vrr(SlotSmem<C>& s, int g)
                 }
             }
         }
+    }
+}
+
+template <class C>
+B2_HD void phase_vrr(SlotSmem<C>& s, int g)
+{
+    for (int task = g; task < 3 * C::NR; task += C::G) {
+        int r = task / 3, x = task - 3 * r;
+        vrr_one<C>(s, 0, r, x);
     }
 }
 
@@ -381,13 +430,13 @@ struct PartDispatch<C, C::NP> {
 
 // Phase D: every thread of the slot
 template <class C>
-B2_HD void phase_accumulate(const SlotSmem<C>& s, ThreadCtx<C>& t, double ABx, double ABy, double ABz)
+B2_HD void phase_accumulate(const SlotSmem<C>& s, ThreadCtx<C>& t, double ABx, double ABy, double ABz, int b = 0)
 {
     for (int r = 0; r < C::NR; r++) {
         double gx[C::NI1 * C::NJ1], gy[C::NI1 * C::NJ1], gz[C::NI1 * C::NJ1];
-        hrr_dir<C>(s.H[0][r], t.kx, t.lx, ABx, gx);
-        hrr_dir<C>(s.H[1][r], t.ky, t.ly, ABy, gy);
-        hrr_dir<C>(s.H[2][r], t.kz, t.lz, ABz, gz);
+        hrr_dir<C>(s.H[b][0][r], t.kx, t.lx, ABx, gx);
+        hrr_dir<C>(s.H[b][1][r], t.ky, t.ly, ABy, gy);
+        hrr_dir<C>(s.H[b][2][r], t.kz, t.lz, ABz, gz);
         PartDispatch<C, 0>::run(t.p, t.v, gx, gy, gz);
     }
 }
