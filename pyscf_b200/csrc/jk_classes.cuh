@@ -82,10 +82,10 @@ __global__ void __launch_bounds__(TpqCfg<C>::NT) jk_tpq_kernel(const KParams P)
     if (bx < P.nbra) tpq_block<C, SR>(P, bx, blockIdx.y, blockIdx.z);
 }
 #ifndef B2_MINB
-#define B2_MINB 1   // resident CTAs per SM the register allocator must leave room for (tuning knob)
+#define B2_MINB 1   // resident CTAs per SM the register allocator must leave room for, CTAs of <= 192 threads (tuning knob)
 #endif
 template <class C, bool SR>
-__global__ void __launch_bounds__(GroupCfg<C>::NT, B2_MINB) jk_class_kernel(const KParams P)
+__global__ void __launch_bounds__(GroupCfg<C>::NT, GroupCfg<C>::NT <= 192 ? B2_MINB : 1) jk_class_kernel(const KParams P)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     BlockSmem<C>& sm = *reinterpret_cast<BlockSmem<C>*>(smraw);

@@ -9,6 +9,7 @@ import numpy as np
 from pyscf_b200 import gto
 from pyscf_b200.gto.mole import geometry
 from pyscf_b200.jk import VHFOpt
+from pyscf_b200 import lib as _lib
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--geom', default='benzene')
@@ -36,6 +37,19 @@ for path in a.libs:
             ref = (vj, vk)
         err = max(abs(vj - ref[0]).max(), abs(vk - ref[1]).max())
         out[name] = {'best_ms': min(ms), 'mean_ms': float(np.mean(ms)), 'max_abs_dev_vs_first': float(err)}
+        # per-class times, classes serialised (CUDA events around each class launch)
+        h = opt.handle
+        h.lib.b200jk_set_profile(h._h, 1)
+        acc = np.zeros(100)
+        for _ in range(3):
+            opt.get_jk(dm)
+            cm = np.zeros(100)
+            h.lib.b200jk_get_class_times(h._h, _lib.dptr(cm), 100)
+            acc = cm if acc.sum() == 0 else np.minimum(acc, cm)
+        names = ['ss', 'ps', 'pp', 'ds', 'dp', 'dd', 'fs', 'fp', 'fd', 'ff']
+        out[name]['class_ms'] = {names[cb] + '|' + names[ck]: float(acc[cb * 10 + ck]) for cb in range(10) for ck in range(cb + 1)
+                                 if acc[cb * 10 + ck] > 0}
+        out[name]['class_ms_sum'] = float(acc.sum())
         print('%-28s best %8.3f ms  mean %8.3f ms  |dJK| vs first %.1e' % (name, min(ms), np.mean(ms), err), flush=True)
         opt.close()
     except Exception as e:   # a variant that fails to launch must not hide the others
