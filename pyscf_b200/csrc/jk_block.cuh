@@ -208,6 +208,7 @@ void group_proc(const KParams& P, BlockSmem<C>& sm, int grp, int nk, int bx,
                     if (L.valid) {
                         SlotSmem<C>& s = sm.slot[L.slot];
                         const int nq = s.nq, nkp = s.nprim_k;
+                        B2_NOUNROLL
                         for (int task = L.t.g; task < C::PB * C::NR; task += C::G) {
                             const int b = task / C::NR, r = task - b * C::NR;
                             const int e = e0 + b;
@@ -228,6 +229,7 @@ void group_proc(const KParams& P, BlockSmem<C>& sm, int grp, int nk, int bx,
                     if (L.valid) {
                         SlotSmem<C>& s = sm.slot[L.slot];
                         const int nq = s.nq;
+                        B2_NOUNROLL
                         for (int task = L.t.g; task < C::PB * 3 * C::NR; task += C::G) {
                             const int b = task / (3 * C::NR), rem = task - b * (3 * C::NR);
                             const int r = rem / 3, x = rem - 3 * r;
@@ -242,6 +244,7 @@ void group_proc(const KParams& P, BlockSmem<C>& sm, int grp, int nk, int bx,
                     if (L.valid) {
                         SlotSmem<C>& s = sm.slot[L.slot];
                         const int nq = s.nq;
+                        B2_NOUNROLL
                         for (int b = 0; b < C::PB; b++)
                             if (e0 + b < nq) phase_accumulate<C>(s, L.t, sm.bra.ABx, sm.bra.ABy, sm.bra.ABz, b);
                     }

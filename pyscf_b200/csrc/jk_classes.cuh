@@ -65,7 +65,8 @@ template <int LI, int LJ, int LK, int LL>
 struct ClassCfg {
     static constexpr int NP = choose_np(ncart(LI), ncart(LJ), ncart(LK) * ncart(LL));
     using C1 = QClass<LI, LJ, LK, LL, NP>;
-    static constexpr int PB = choose_pb(C1::G, C1::NR, 3 * C1::NR * C1::HSP * 8, GroupCfg<C1>::NSLOT);
+    // (ff| bra classes stay at one primitive quartet per round: their batched kernels take the NVVM optimiser tens of minutes)
+    static constexpr int PB = (LI + LJ >= 6) ? 1 : choose_pb(C1::G, C1::NR, 3 * C1::NR * C1::HSP * 8, GroupCfg<C1>::NSLOT);
     using C = QClass<LI, LJ, LK, LL, NP, PB>;
     using GC = GroupCfg<C>;
     static constexpr int NT = GC::NT;
@@ -82,10 +83,14 @@ __global__ void __launch_bounds__(TpqCfg<C>::NT) jk_tpq_kernel(const KParams P)
     if (bx < P.nbra) tpq_block<C, SR>(P, bx, blockIdx.y, blockIdx.z);
 }
 #ifndef B2_MINB
-#define B2_MINB 1   // resident CTAs per SM the register allocator must leave room for, CTAs of <= 192 threads (tuning knob)
+#define B2_MINB 0   // > 0: resident CTAs per SM the register allocator must leave room for, CTAs of <= 192 threads (tuning knob)
 #endif
 template <class C, bool SR>
+#if B2_MINB > 0
 __global__ void __launch_bounds__(GroupCfg<C>::NT, GroupCfg<C>::NT <= 192 ? B2_MINB : 1) jk_class_kernel(const KParams P)
+#else
+__global__ void __launch_bounds__(GroupCfg<C>::NT) jk_class_kernel(const KParams P)
+#endif
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     BlockSmem<C>& sm = *reinterpret_cast<BlockSmem<C>*>(smraw);
