@@ -82,15 +82,36 @@ __global__ void __launch_bounds__(TpqCfg<C>::NT) jk_tpq_kernel(const KParams P)
     const int bx = blockIdx.x * P.shard_world + P.shard_rank;
     if (bx < P.nbra) tpq_block<C, SR>(P, bx, blockIdx.y, blockIdx.z);
 }
+// Register cap per class.  Most block kernels need 180-255 registers, i.e. ONE 192-thread CTA (6 warps) per SM; capping
+// them at 168 registers (two resident CTAs) wins 10-35 % on most classes and loses 15-40 % on the few whose working set
+// does not fit (spills): measured per class on B200, profiles/r01_ab_direct_variants.txt (column minb2).  The cap is applied
+// where it measured faster; the other kernels keep the plain bound (an explicit minBlocks = 1 is NOT equivalent: it makes
+// ptxas schedule seven classes 30-50 % slower).  B2_MINB = 0 / 2 forces one choice for every class (A/B builds).
 #ifndef B2_MINB
-#define B2_MINB 0   // > 0: resident CTAs per SM the register allocator must leave room for, CTAs of <= 192 threads (tuning knob)
+#define B2_MINB -1   // -1: per-class table below; 0: never cap; 2: cap every kernel of <= 192 threads
 #endif
+constexpr bool class_caps_registers(int li, int lj, int lk, int ll)
+{
+    if (B2_MINB == 0) return false;
+    if (B2_MINB > 0) return true;
+    if (li == 3 && lj == 1) return false;                                   // (fp| bras: 254 registers, spill when capped
+    if (li == 3 && lj == 2 && lk == 1 && ll == 0) return false;            // (fd|ps)
+    if (li == 3 && lj == 2 && lk == 3 && ll == 1) return false;            // (fd|fp)
+    if (li == 2 && lj == 0 && lk == 1 && ll == 1) return false;            // (ds|pp)
+    if (li == 1 && lj == 1 && lk == 1 && ll == 1) return false;            // (pp|pp)
+    return true;
+}
 template <class C, bool SR>
-#if B2_MINB > 0
-__global__ void __launch_bounds__(GroupCfg<C>::NT, GroupCfg<C>::NT <= 192 ? B2_MINB : 1) jk_class_kernel(const KParams P)
-#else
 __global__ void __launch_bounds__(GroupCfg<C>::NT) jk_class_kernel(const KParams P)
-#endif
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    BlockSmem<C>& sm = *reinterpret_cast<BlockSmem<C>*>(smraw);
+    const int bx = blockIdx.x * P.shard_world + P.shard_rank;
+    if (bx < P.nbra) jk_block<C, SR>(P, bx, blockIdx.y, sm);
+}
+// the same kernel compiled for two resident CTAs per SM (<= 168 registers at 192 threads)
+template <class C, bool SR>
+__global__ void __launch_bounds__(GroupCfg<C>::NT, 2) jk_class_kernel_2cta(const KParams P)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     BlockSmem<C>& sm = *reinterpret_cast<BlockSmem<C>*>(smraw);
@@ -109,15 +130,18 @@ typedef int b2_stream_t;
 template <class C, bool SR>
 void launch_block_kernel(const KParams& P, dim3 grid, int nt, size_t smem, b2_stream_t st)
 {
+    void (*kern)(const KParams) = nullptr;      // only the chosen entry point is instantiated
+    if constexpr (GroupCfg<C>::NT <= 192 && class_caps_registers(C::LI, C::LJ, C::LK, C::LL)) kern = jk_class_kernel_2cta<C, SR>;
+    else kern = jk_class_kernel<C, SR>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(jk_class_kernel<C, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
         // leave half of the 228 KB for L1 (Rys tables, density blocks); the other half lets several CTAs co-reside
-        cudaFuncSetAttribute(jk_class_kernel<C, SR>, cudaFuncAttributePreferredSharedMemoryCarveout, B2_CARVEOUT);
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, B2_CARVEOUT);
         configured = true;
     }
-    jk_class_kernel<C, SR><<<grid, nt, smem, st>>>(P);
+    kern<<<grid, nt, smem, st>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw std::runtime_error(std::string("jk_class_kernel launch: ") + cudaGetErrorString(e));
 }
