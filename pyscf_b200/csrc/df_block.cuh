@@ -49,10 +49,17 @@ void j3c_block(const J3cParams& P, int bx, int by, BlockSmem<C>& sm)
         LaneCtx<C>& L = B2_CTX(tid);
         L.grp = tid / GC::TG;
         L.lt = tid % GC::TG;
-        int sl = L.lt / GC::GP, g = L.lt % GC::GP;
-        L.valid = (sl < GC::QPG) && (g < C::G);
-        L.slot = L.grp * GC::QPG + (sl < GC::QPG ? sl : 0);
-        thread_decode<C>(L.t, g < C::G ? g : 0);
+        if constexpr (GC::PPW) {
+            int sl, g;
+            L.valid = GC::decode(L.lt, sl, g);
+            L.slot = L.grp * GC::QPG + sl;
+            thread_decode<C>(L.t, g);
+        } else {
+            int sl = L.lt / GC::GP, g = L.lt % GC::GP;
+            L.valid = (sl < GC::QPG) && (g < C::G);
+            L.slot = L.grp * GC::QPG + (sl < GC::QPG ? sl : 0);
+            thread_decode<C>(L.t, g < C::G ? g : 0);
+        }
         L.t.q = L.slot;
         if (tid == 0) {
             sm.bra.ABx = bpair.ABx; sm.bra.ABy = bpair.ABy; sm.bra.ABz = bpair.ABz;

@@ -40,13 +40,25 @@ struct KParams {
 
 constexpr int pow2ceil(int x) { int p = 1; while (p < x) p *= 2; return p; }
 
+#ifndef B2_PPW
+#define B2_PPW 0             // 1: "part per warp" lane layout for classes whose bra block is split into NP > 1 parts
+#endif
+
+// Lane layout of one thread group.
+//  * default: a quartet owns G = NKL * NP consecutive lanes (part index slowest); QPG = 32 / G quartets share a warp when
+//    G <= 32, otherwise the quartet gets whole warps.  Lanes of different PARTS then sit in one warp, and since every part
+//    is different straight-line code (compile-time Cartesian indices of its j components) the warp runs the root sum
+//    once per part it holds (ncu: 20 of 32 threads active per instruction in (fd|dp)).
+//  * PPW (B2_PPW, classes with NP > 1 and NKL <= 32): a group is NP warps, warp w holds part w of QPG = 32 / NKL quartets,
+//    so no warp ever mixes parts.  Logical lane id inside a quartet stays g = part * NKL + (c,d).
 template <class C>
 struct GroupCfg {
     static constexpr int G = C::G;
-    static constexpr int GP = G <= 32 ? G : ((G + 31) / 32) * 32;              // lanes reserved per quartet
-    static constexpr int GW = (GP + 31) / 32;                                // warps per group
+    static constexpr bool PPW = (B2_PPW != 0) && C::NP > 1 && C::NKL <= 32 && C::NP <= 8;
+    static constexpr int GP = G <= 32 ? G : ((G + 31) / 32) * 32;              // lanes reserved per quartet (default layout)
+    static constexpr int GW = PPW ? C::NP : (GP + 31) / 32;                  // warps per group
     static constexpr int TG = GW * 32;                                       // threads per group
-    static constexpr int QPG = GP <= 32 ? 32 / GP : 1;                       // quartets in flight per group
+    static constexpr int QPG = PPW ? 32 / C::NKL : (GP <= 32 ? 32 / GP : 1); // quartets in flight per group
     static constexpr int NG0 = B2_CTA_THREADS / TG;
     static constexpr int NG1 = NG0 < 1 ? 1 : (NG0 > 8 ? 8 : NG0);
     static constexpr int NG2 = (NG1 * QPG > 64) ? ((64 / QPG) < 1 ? 1 : 64 / QPG) : NG1;  // groups per CTA, <= 64 quartet slots
@@ -54,6 +66,15 @@ struct GroupCfg {
     static constexpr int NG = NGC < 1 ? 1 : (NGC < NG2 ? NGC : NG2);
     static constexpr int NT = NG * TG;
     static constexpr int NSLOT = NG * QPG;
+    // PPW layout: lane lt of a group -> (quartet sub-slot sl, logical lane g inside the quartet); false for idle lanes
+    static B2_HD bool decode(int lt, int& sl, int& g)
+    {
+        const int w = lt / 32, l = lt % 32;
+        sl = l / C::NKL;
+        g = w * C::NKL + l % C::NKL;
+        if (sl >= QPG) { sl = 0; g = 0; return false; }
+        return true;
+    }
 };
 
 template <class C>
@@ -336,10 +357,17 @@ void jk_block(const KParams& P, int bx, int by, BlockSmem<C>& sm)
         LaneCtx<C>& L = B2_CTX(tid);
         L.grp = tid / GC::TG;
         L.lt = tid % GC::TG;
-        int sl = L.lt / GC::GP, g = L.lt % GC::GP;
-        L.valid = (sl < GC::QPG) && (g < C::G);
-        L.slot = L.grp * GC::QPG + (sl < GC::QPG ? sl : 0);
-        thread_decode<C>(L.t, g < C::G ? g : 0);
+        if constexpr (GC::PPW) {
+            int sl, g;
+            L.valid = GC::decode(L.lt, sl, g);
+            L.slot = L.grp * GC::QPG + sl;
+            thread_decode<C>(L.t, g);
+        } else {
+            int sl = L.lt / GC::GP, g = L.lt % GC::GP;
+            L.valid = (sl < GC::QPG) && (g < C::G);
+            L.slot = L.grp * GC::QPG + (sl < GC::QPG ? sl : 0);
+            thread_decode<C>(L.t, g < C::G ? g : 0);
+        }
         L.t.q = L.slot;
         B2_UNROLL
         for (int e = 0; e < C::NV; e++) L.jij[e] = 0.0;

@@ -153,3 +153,22 @@ def test_emulated_screening_and_errors(emu_lib):
     qo = O.q_cond(mol)
     big = qo > 1e-12  # negligible pairs are dropped on the device side (reported as the 1e-100 floor)
     assert q.shape == qo.shape and abs(np.log(q[big] / qo[big])).max() < 1e-9  # s,p: identical to CVHFnr_int2e_q_cond
+
+
+def test_emulated_experimental_layouts(emu_lib, emu_lib_experimental):
+    """Primitive batching (QClass::PB) and the part-per-warp lane layout (GroupCfg::PPW) are compile-time options that are
+    off in the shipped library until measured; they must give the same J/K as the default layout (same primitive order,
+    so only the order of the reductions differs) for d/f shells, hermi 0/1 and the erf / erfc operators."""
+    for atom, basis, omega in [(H2O, 'cc-pvdz', None), ('He 0 0 0; Ne 1.2 0.3 0', 'cc-pvtz', None), (H2O, 'cc-pvdz', -0.4),
+                               ('O 0 0 0; O 0 0 1.2', 'cc-pvdz', 0.7)]:
+        mol = gto.M(atom=atom, basis=basis)
+        nao = mol.nao
+        np.random.seed(3)
+        dms = np.random.random((2, nao, nao))
+        a = VHFOpt(mol, omega=omega, libpath=emu_lib_experimental).get_jk(dms, hermi=0)
+        b = VHFOpt(mol, omega=omega, libpath=emu_lib).get_jk(dms, hermi=0)
+        assert abs(a[0] - b[0]).max() < 1e-11 and abs(a[1] - b[1]).max() < 1e-11
+        d = dms[0] + dms[0].T
+        a = VHFOpt(mol, omega=omega, libpath=emu_lib_experimental).get_jk(d, hermi=1)
+        r = O.get_jk(mol, d, omega=omega)
+        assert abs(a[0] - r[0]).max() < 1e-10 and abs(a[1] - r[1]).max() < 1e-10
