@@ -369,7 +369,7 @@ def cpu_baseline_df(mol, dm, c_occ, workload):
     packed = rng.standard_normal((rows, nao * (nao + 1) // 2))
     t = time.perf_counter()
     vj = dmtril.dot(packed.T).dot(packed)
-    buf = np.einsum('pij,jk->pki', eri1, orbo, optimize=True) if False else np.matmul(eri1, orbo)   # (P, nao, nocc)
+    buf = np.matmul(eri1, orbo)   # (P, nao, nocc)
     buf = buf.transpose(0, 2, 1).reshape(-1, nao)
     vk = buf.T.dot(buf)
     dt = (time.perf_counter() - t) * naux / rows
@@ -442,11 +442,15 @@ def run_reference(args, rank, world):
     base['value'] = v
     out = {'impl': 'reference', 'metric': 'J/K Fock-build wall-s/iter', 'value': v, 'unit': 's', 'n_gpus': world,
            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': v * 1e3, 'higher_is_better': False,
-           'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+           'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
            'config': {'workload': args.workload, 'molecule': w['geom'], 'basis': w['basis'], 'nao': mol.nao,
-                      'path': ('DF J/K' if w['kind'] == 'df' else '4-center direct J/K (hermi=1)'), 'direct_scf_tol': 1e-13,
-                      'note': 'reference CPU path = oracle port (libcint is not vendored in the reference tree; '
-                              'see DESIGN.md)'},
+                      'path': ('DF J/K (reference algebra on the host)' if w['kind'] == 'df'
+                               else '4-center direct J/K (hermi=1, with_j, with_k)'), 'direct_scf_tol': 1e-13,
+                      'dm': 'SCF-like 2*C_occ*C_occ^T, orthonormal random C_occ, seed 1',
+                      'parallelism': 'host cores of rank 0 (OpenMP), no GPU',
+                      'note': 'reference CPU path: the reference driver/screening/digestion compiled from its own sources '
+                              '(oracle/_ref) around the oracle integral function; libcint itself is not vendored in the '
+                              'reference tree (DESIGN.md section 2)'},
            'cpu_baseline': base,
            'e2e': {'value': v, 'unit': 's', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(out))
