@@ -12,13 +12,24 @@
 
 namespace b200jk {
 
+// compile-time tuning knobs of the thread-per-quartet kernels (A/B libraries: tools/build_variant.sh)
+#ifndef B2_TPQ_NT
+#define B2_TPQ_NT 128        // threads per CTA
+#endif
+#ifndef B2_TPQ_PSLICE
+#define B2_TPQ_PSLICE 8      // bra primitive pairs per CTA slice
+#endif
+#ifndef B2_TPQ_KCHUNK
+#define B2_TPQ_KCHUNK 512    // ket pairs examined per CTA (upper bound)
+#endif
+
 template <class C>
 struct TpqCfg {
     static constexpr int NAB = C::NI * C::NJ, NKL = C::NKL, NOUT = NAB * NKL;
     static constexpr bool eligible = (NOUT <= 36) && (C::NR <= 3) && (C::NP == 1);
-    static constexpr int NT = 128;
-    static constexpr int KCHUNK = 512;
-    static constexpr int PSLICE = 8;      // bra primitive pairs per CTA slice (blockIdx.z): bounds the serial work of a thread
+    static constexpr int NT = B2_TPQ_NT;
+    static constexpr int KCHUNK = B2_TPQ_KCHUNK;
+    static constexpr int PSLICE = B2_TPQ_PSLICE;      // bra primitive pairs per CTA slice (blockIdx.z): bounds the serial work of a thread
     static constexpr int GI = C::LI + 1, GJ = C::LJ + 1, GK = C::LK + 1, GL = C::LL + 1;
     static constexpr int GSZ = GI * GJ * GK * GL;
 };
