@@ -19,6 +19,9 @@ namespace b200jk {
 #ifndef B2_TPQ_PSLICE
 #define B2_TPQ_PSLICE 8      // bra primitive pairs per CTA slice
 #endif
+#ifndef B2_TPQ_KOUTER
+#define B2_TPQ_KOUTER 0      // 1: ket primitive loop outside the bra primitive loop (each thread loads its own ket primitive once
+#endif                       //    per ket primitive instead of once per primitive QUARTET; the bra primitive is warp-uniform)
 #ifndef B2_TPQ_KCHUNK
 #define B2_TPQ_KCHUNK 512    // ket pairs examined per CTA (upper bound)
 #endif
@@ -93,10 +96,17 @@ B2_HD void tpq_eri(const KParams& P, const ShellPair& bp, const ShellPair& kp, i
     using T = TpqCfg<C>;
     B2_UNROLL
     for (int e = 0; e < T::NOUT; e++) v[e] = 0.0;
+#if B2_TPQ_KOUTER
+    for (int ik = 0; ik < kp.nprim; ik++) {
+        const PrimPair k = load_prim(P.prims + kp.prim_off + ik);
+        for (int ib = ib0; ib < ib1; ib++) {
+            const PrimPair b = load_prim(P.prims + bp.prim_off + ib);
+#else
     for (int ib = ib0; ib < ib1; ib++) {
         const PrimPair b = load_prim(P.prims + bp.prim_off + ib);
         for (int ik = 0; ik < kp.nprim; ik++) {
             const PrimPair k = load_prim(P.prims + kp.prim_off + ik);
+#endif
             double p = b.p, q = k.p;
             double PQx = b.Px - k.Px, PQy = b.Py - k.Py, PQz = b.Pz - k.Pz;
             double pq = p + q;

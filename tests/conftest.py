@@ -28,7 +28,7 @@ def emu_lib():
 
 @pytest.fixture(scope='session')
 def emu_lib_experimental():
-    """The emulation compiled with the experimental lane layouts on (-DB2_PBMAX=4 -DB2_PPW=1), see DESIGN.md §4.1."""
+    """The emulation compiled with the experimental lane layouts on (-DB2_PBMAX=4 -DB2_PPW=1 -DB2_TPQ_KOUTER=1), see DESIGN.md §4.1."""
     import subprocess
     subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'pyscf_b200', 'csrc'), 'emu_x'])
     return os.path.join(ROOT, 'tests', 'emu', 'libb200jk_emu_pbppw.so')
