@@ -103,13 +103,12 @@ class ClockSampler(threading.Thread):
                 'samples': len(sm)}
 
 
-def algorithmic_counts(mol, opt):
-    """Frozen algorithmic work of one direct build for `mol`: unique Cartesian ERIs of the
-    unscreened upper bound, FP64 flops = per class n_quartet*n_cart_eri*(nprim_avg*nroots*3 + 12), bytes = D+J+K+pairs."""
+def algorithmic_bytes(opt):
+    """Algorithmic HBM bytes of one direct build: D, J and K once each (3 n^2 doubles) plus the shell-pair
+    records the kernels stream (48 B of each 64-byte record are payload)."""
     st = opt.stats()
     n = st['n_sph']
-    bytes_alg = 3 * n * n * 8 + st['n_pairs'] * 48
-    return bytes_alg
+    return 3 * n * n * 8 + st['n_pairs'] * 48
 
 
 def run_ours(args, rank, world):
@@ -249,7 +248,7 @@ def run_ours(args, rank, world):
         peak = ctypes.c_double(0)
         h.lib.b200jk_fp64_peak(h._h, ctypes.byref(peak))
         flops, n_eri = direct_jk_flops(mol)
-        bytes_alg = algorithmic_counts(mol, eng)
+        bytes_alg = algorithmic_bytes(eng)
         fp64_ach = flops / world / (kernel_ms * 1e-3) / 1e12
         roof = {'bound': 'fp64', 'achieved': fp64_ach, 'peak': peak.value, 'unit': 'TFLOP/s',
                 'frac': fp64_ach / peak.value if peak.value else None, 'traffic': None,
