@@ -97,10 +97,12 @@ def get_veff_uhf(get_jk, mol, dm, dm_last=None, vhf_last=None, hermi=1, direct_s
     vj = vj[0] + vj[1]
     vhf = vj - vk
     if not incremental:
-        return tag_array(vhf, ecoul=np.einsum('nij,ji->', dm, vj).real * .5)
+        if dm.ndim == 3:      # a single (alpha, beta) pair; batches of pairs carry no energy tag (uhf.py:1076-1078)
+            vhf = tag_array(vhf, ecoul=np.einsum('nij,ji->', dm, vj).real * .5)
+        return vhf
     assert vhf_last is not None
     vhf = vhf + np.asarray(vhf_last)
-    if hasattr(vhf_last, 'ecoul'):
+    if hasattr(vhf_last, 'ecoul') and dm.ndim == 3:
         ecoul = (np.einsum('nij,ji->', np.asarray(dm_last), vj).real + np.einsum('nij,ji->', ddm, vj).real * .5
                  + vhf_last.ecoul)
         vhf = tag_array(vhf, ecoul=ecoul)

@@ -116,6 +116,24 @@ def test_short_range_jk_631g():
     assert abs(O.fp(np.array([vj, vk])) - 25.317344717490613) < 1e-9
 
 
+def test_direct_jk_631g_and_veff_norms(h2o):
+    # pyscf/scf/test/test_vhf.py:158-173: K ('jk->s1il') and J ('ji->s1kl') of a symmetrised random density, H2O/6-31G
+    mol = gto.M(atom=H2O, basis='6-31g')
+    np.random.seed(1)
+    dm = np.random.random((mol.nao, mol.nao))
+    dm = dm + dm.T
+    vj, vk = O.get_jk(mol, dm)
+    assert abs(O.fp(vk) - 5.0067176755619975) < 1e-9 and abs(O.fp(vj) - 48.61070262547175) < 1e-9
+    # pyscf/scf/test/test_rhf.py:453-460: || J - K/2 || of two densities, H2O/cc-pVDZ
+    nao = h2o.nao
+    np.random.seed(1)
+    d1 = np.random.random((nao, nao))
+    d2 = np.random.random((nao, nao))
+    d = np.array((d1 + d1.T, d2 + d2.T))
+    vj, vk = O.get_jk(h2o, d)
+    assert abs(np.linalg.norm(vj - .5 * vk) - 199.66041114502335) < 1e-9
+
+
 def test_overlap_is_normalised(h2o):
     s = O.int1e(h2o, 'ovlp')
     assert abs(np.diag(s) - 1).max() < 1e-12

@@ -105,6 +105,41 @@ def _check_rks_df(libpath):
     assert abs(v.vk - (hyb * rk + (alpha - hyb) * rklr)).max() < 1e-9
 
 
+def _check_reference_fingerprints(libpath):
+    # pyscf/scf/test/test_rhf.py:453-460: scf.hf.get_veff of two densities, H2O/cc-pVDZ
+    mol = gto.M(atom=H2O, basis='cc-pvdz')
+    nao = mol.nao
+    np.random.seed(1)
+    d1 = np.random.random((nao, nao))
+    d2 = np.random.random((nao, nao))
+    d = np.array((d1 + d1.T, d2 + d2.T))
+    get_jk = veff.make_get_jk(mol, libpath=libpath)
+    v = veff.get_veff_rhf(get_jk, mol, d)
+    assert abs(np.linalg.norm(v) - 199.66041114502335) < 1e-9
+    # pyscf/df/test/test_df_jk.py:127-133: UHF get_veff through density fitting, dm of shape (2, 4, nao, nao), hermi=0
+    dfobj = DF(mol, 'weigend', libpath=libpath).build()
+    np.random.seed(1)
+    dm = np.random.random((2, 4, nao, nao))
+    vhf = veff.get_veff_uhf(veff.make_get_jk(mol, with_df=dfobj), mol, dm, hermi=0)
+    assert vhf.shape == (2, 4, nao, nao) and abs(np.linalg.norm(vhf) - 413.82341595365853) < 1e-9
+    # pyscf/scf/test/test_vhf.py:158-173: K and J of a symmetrised random density, H2O/6-31G
+    mol = gto.M(atom=H2O, basis='6-31g')
+    np.random.seed(1)
+    dm = np.random.random((mol.nao, mol.nao))
+    dm = dm + dm.T
+    vj, vk = veff.make_get_jk(mol, libpath=libpath)(mol, dm)
+    assert abs(O.fp(vk) - 5.0067176755619975) < 1e-9 and abs(O.fp(vj) - 48.61070262547175) < 1e-9
+
+
+def test_reference_fingerprints_emulated(emu_lib):
+    _check_reference_fingerprints(emu_lib)
+
+
+@pytest.mark.gpu
+def test_reference_fingerprints_gpu():
+    _check_reference_fingerprints(None)
+
+
 def test_incremental_veff_emulated(emu_lib):
     _check_incremental(emu_lib)
 
