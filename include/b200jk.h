@@ -100,6 +100,10 @@ int b200jk_df_stage_times(b200jk_handle h, double* ms, int* count, int n);
  * b200jk_set_shard(rank, world) was called BEFORE b200jk_df_build, in which case only this rank's rows are built
  * (the 3-center integrals are computed in bounded batches of AO shell pairs and multiplied by this rank's rows of L^-1). */
 int b200jk_df_local_rows(b200jk_handle h, int* row0, int* nrow);
+/* Use a tensor made elsewhere instead of b200jk_df_build: cderi[naux][nao(nao+1)/2] host buffer in the reference layout
+ * (mf.with_df._cderi = ndarray, pyscf/df/df.py:116, pyscf/df/test/test_df_jk.py:135-142).  Honours b200jk_set_shard (only this
+ * rank's rows are uploaded).  b200jk_df_direct_j is not available on such a handle (no auxiliary basis, no metric). */
+int b200jk_df_set_cderi(b200jk_handle h, const double* cderi, int naux, int nao);
 /* Rows [r0, r0+nr) (LOCAL indices) of the device-resident tensor, reference layout cderi[naux, nao(nao+1)/2]
  * (pyscf/df/incore.py:134-136; what DF.loop() yields, pyscf/df/df.py:214-242). */
 int b200jk_df_get_cderi(b200jk_handle h, double* out, int r0, int nr);

@@ -748,6 +748,41 @@ extern "C" int b200jk_df_naux(b200jk_handle h, int* naux)
     return 0;
 }
 
+// A tensor made elsewhere (PySCF's with_df._cderi, an earlier run) handed to the handle instead of b200jk_df_build:
+// cderi[naux][nao(nao+1)/2], the reference layout (pyscf/df/incore.py:134-136; assignment test pyscf/df/test/test_df_jk.py:135-142).
+// With a shard set, only this rank's rows [naux r/w, naux (r+1)/w) are copied to the device.  No auxiliary basis and no
+// metric are attached, so the integral-direct J (b200jk_df_direct_j) is not available on such a handle.
+extern "C" int b200jk_df_set_cderi(b200jk_handle h, const double* cderi, int naux, int nao)
+{
+    if (!h) return 1;
+    try {
+        if (!cderi || naux < 1) throw std::runtime_error("bad arguments");
+        if (nao != h->nsph) throw std::runtime_error("nao does not match the basis of this handle");
+        if (h->df) { df_free(h->df); h->df = nullptr; }
+        DFState* d = new DFState();
+        h->df = d; h->df_free = df_free;
+#ifndef B200JK_EMULATE
+        CK(cudaSetDevice(h->device));
+        cudaStream_t st = h->stream;
+        CKB(cublasCreate(&d->cublas));
+        CKS(cusolverDnCreate(&d->cusolver));
+#else
+        stream_t st = 0;
+#endif
+        d->npair = (long)nao * (nao + 1) / 2;
+        d->naux = naux;
+        const int bw = h->shard_world, br = h->shard_rank;
+        const int r_lo = (int)((long)naux * br / bw), r_hi = (int)((long)naux * (br + 1) / bw);
+        d->build_rank = br; d->build_world = bw; d->row0 = r_lo; d->nrow = r_hi - r_lo;
+        d->d_cderi = (double*)dev_alloc((size_t)std::max(d->nrow, 1) * d->npair * 8);
+        if (d->nrow > 0) h2d(d->d_cderi, cderi + (size_t)r_lo * d->npair, (size_t)d->nrow * d->npair * 8, st);
+#ifndef B200JK_EMULATE
+        CK(cudaStreamSynchronize(st));
+#endif
+    } catch (std::exception& e) { set_err(h, e.what()); return 2; }
+    return 0;
+}
+
 extern "C" int b200jk_df_local_rows(b200jk_handle h, int* row0, int* nrow)
 {
     if (!h || !h->df || !row0 || !nrow) { set_err(h, "call b200jk_df_build first"); return 1; }

@@ -28,6 +28,7 @@ class DF:
         self._handle = None
         self._vjopt = None         # handle holding only the factorised metric (integral-direct J, get_j)
         self._rsh_df = {}          # omega -> DF (pyscf/df/df.py:298-333 range_coulomb)
+        self._cderi_in = None      # tensor assigned by the caller (ndarray or .npy path), used instead of building one
         self.omega = None
         self.lindep = 1e-7         # pyscf/df/incore.py:30-33 LINEAR_DEP_THR
         self.blockdim = 240        # pyscf/df/df.py:95 (loop() default block size)
@@ -40,6 +41,8 @@ class DF:
     # ---- construction ------------------------------------------------------------------------------
     def build(self):
         mol = self.mol
+        if self._cderi_in is not None:
+            return self._build_from_cderi()
         if self.auxmol is None:
             self.auxmol = make_auxmol(mol, self.auxbasis)
         aux = self.auxmol
@@ -57,6 +60,33 @@ class DF:
         self.nao = int(mol.ao_loc_nr(cart=False)[-1])
         self.set_k_engine(self.k_engine, self.k_slices)
         return self
+
+    def _build_from_cderi(self):
+        """Upload an assigned tensor (mf.with_df._cderi = ndarray | 'file.npy'; pyscf/df/df.py:116-118,
+        pyscf/df/test/test_df_jk.py:135-142) instead of computing 3-center integrals."""
+        mol = self.mol
+        c = self._cderi_in
+        if isinstance(c, str):
+            c = np.load(c, mmap_mode='r')
+        nao = int(mol.ao_loc_nr(cart=False)[-1])
+        npair = nao * (nao + 1) // 2
+        if c.ndim != 2 or c.shape[1] != npair:
+            raise RuntimeError('cderi must have shape (naux, nao*(nao+1)/2) = (*, %d), got %s' % (npair, c.shape))
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        h = _lib.Handle(mol._atm, mol._bas, np.array(mol._env, dtype=np.float64), device=self.device, libpath=self._libpath)
+        if self.shard is not None:
+            h.check(h.lib.b200jk_set_shard(h._h, int(self.shard[0]), int(self.shard[1])), 'b200jk_set_shard')
+        h.check(h.lib.b200jk_df_set_cderi(h._h, _lib.dptr(c), c.shape[0], nao), 'b200jk_df_set_cderi')
+        self._handle = h
+        self.nao = nao
+        self.set_k_engine(self.k_engine, self.k_slices)
+        return self
+
+    def save(self, path):
+        """Write the tensor to `path` (.npy, the reference layout) — the role of DF._cderi_to_save (pyscf/df/df.py:112-118,
+        which writes HDF5; h5py is not a dependency here).  Reload with `DF(mol)._cderi = path`."""
+        np.save(path, self._cderi)
+        return path
 
     def set_k_engine(self, engine='tcgen05', nslices=7):
         """'tcgen05' (int8-slice tensor-core GEMMs, default) or 'dgemm' (cuBLAS FP64 yardstick)."""
@@ -107,6 +137,14 @@ class DF:
     def _cderi(self):
         return np.vstack(list(self.loop()))
 
+    @_cderi.setter
+    def _cderi(self, value):
+        # assigning a tensor discards whatever was built (reset() keeps the assignment, like the reference keeps _cderi)
+        if self._handle is not None:
+            self._handle.close()
+            self._handle = None
+        self._cderi_in = value
+
     def range_coulomb(self, omega):
         key = float(omega)
         if key not in self._rsh_df:
@@ -140,6 +178,8 @@ class DF:
     def get_j(self, dm, hermi=0, direct_scf_tol=1e-13):
         """Integral-direct J without the three-index tensor: rho = j2c^-1 (P|ij) D_ji, J_ij = (ij|P) rho_P, two passes
         over the 3-center integrals on the GPU (df_jk.get_j, pyscf/df/df_jk.py:415-506)."""
+        if self._cderi_in is not None:     # an assigned tensor has no auxiliary basis / metric attached: J from the tensor
+            return self.get_jk(dm, hermi, True, False, direct_scf_tol)[0]
         h = self._handle or getattr(self, '_vjopt', None) or self._prepare_j()
         nao = self.nao
         dm = np.asarray(dm)
@@ -156,7 +196,7 @@ class DF:
     def get_jk(self, dm, hermi=1, with_j=True, with_k=True, direct_scf_tol=1e-13, omega=None):
         if omega is not None and omega != 0 and omega != self.omega:
             return self.range_coulomb(omega).get_jk(dm, hermi, with_j, with_k, direct_scf_tol)
-        if not with_k and self._handle is None and self.shard is None:
+        if not with_k and self._handle is None and self.shard is None and self._cderi_in is None:
             # J only and no tensor yet: integral-direct J (pyscf/df/df_jk.py:282-285)
             return self.get_j(dm, hermi, direct_scf_tol), None
         if self._handle is None:

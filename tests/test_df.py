@@ -73,6 +73,67 @@ def test_df_long_range_k_against_exact_4center(emu_lib):
     assert 1e-4 < abs(vk - ek).max() < 0.2 and abs(vj - ej).max() < 0.1   # fitting error of the full operator, for scale
 
 
+def _check_assign_cderi(libpath, tmpdir):
+    """mf.with_df._cderi = ndarray (pyscf/df/df.py:116-118; pyscf/df/test/test_df_jk.py:135-142 assigns an exact factorisation
+    of the 4-center integrals and recovers the non-DF energy): a tensor made elsewhere is uploaded instead of built."""
+    import scipy.linalg
+    mol = gto.M(atom=H2O, basis='6-31g')
+    nao = mol.nao
+    # (1) exact factorisation of (ij|kl): DF algebra on it must reproduce the exact 4-center J/K
+    eri = O.int2e(mol)
+    i, j = np.tril_indices(nao)
+    e4 = eri[i, j][:, i, j]                      # aosym s4 as a (npair, npair) matrix
+    w, u = scipy.linalg.eigh(e4)
+    idx = w > 1e-9
+    exact = (u[:, idx] * np.sqrt(w[idx])).T.copy()
+    d = DF(mol, libpath=libpath)
+    d._cderi = exact
+    np.random.seed(5)
+    dm = np.random.random((nao, nao))
+    dm = dm + dm.T
+    vj, vk = d.get_jk(dm)
+    rj, rk = O.get_jk(mol, dm)
+    assert d.get_naoaux() == exact.shape[0]
+    assert abs(vj - rj).max() < 1e-7 and abs(vk - rk).max() < 1e-7          # eigenvalues below 1e-9 were dropped
+    assert abs(d.get_j(dm) - vj).max() < 1e-12                                # J-only goes through the tensor
+    c = np.linalg.qr(np.random.random((nao, 5)))[0]
+    dmo = TaggedDM(2 * c.dot(c.T), mo_coeff=c, mo_occ=np.full(5, 2.0))
+    assert abs(d.get_jk(dmo)[1] - O.get_jk(mol, np.asarray(dmo))[1]).max() < 1e-7   # orbital (tensor-core) K path
+    # (2) round trip of a built tensor through a file: same J/K as the DF object that built it
+    a = DF(mol, 'weigend', libpath=libpath).build()
+    path = a.save(str(tmpdir / 'cderi.npy'))
+    b = DF(mol, libpath=libpath)
+    b._cderi = path
+    ja, ka = a.get_jk(dm)
+    jb, kb = b.get_jk(dm)
+    assert abs(ja - jb).max() < 1e-12 and abs(ka - kb).max() < 1e-12
+    assert abs(b._cderi - a._cderi).max() == 0
+    # (3) row-sharded upload: every rank takes its rows of the assigned tensor, partial J/K add up
+    parts = []
+    for r in range(2):
+        p = DF(mol, libpath=libpath, shard=(r, 2))
+        p._cderi = path
+        p.build()
+        h = p._handle
+        h.check(h.lib.b200jk_set_shard(h._h, r, 2), 'b200jk_set_shard')
+        parts.append(p.get_jk(dm))
+        assert sum(len(blk) for blk in p.loop()) in (a.get_naoaux() // 2, a.get_naoaux() - a.get_naoaux() // 2)
+    assert abs(parts[0][0] + parts[1][0] - ja).max() < 1e-11 and abs(parts[0][1] + parts[1][1] - ka).max() < 1e-11
+    with pytest.raises(RuntimeError):
+        bad = DF(mol, libpath=libpath)
+        bad._cderi = np.zeros((3, 7))
+        bad.build()
+
+
+def test_assign_cderi_emulated(emu_lib, tmp_path):
+    _check_assign_cderi(emu_lib, tmp_path)
+
+
+@pytest.mark.gpu
+def test_assign_cderi_gpu(tmp_path):
+    _check_assign_cderi(None, tmp_path)
+
+
 def _check_direct_j(libpath):
     # integral-direct J (no tensor; df_jk.get_j, pyscf/df/df_jk.py:415-506) == J from the stored tensor;
     # reference fingerprint of the DF J matrix, pyscf/df/test/test_df_jk.py:151
