@@ -82,7 +82,7 @@ def get_jk(mol, dm, hermi=1, vhfopt=None, with_j=True, with_k=True, omega=None):
     return vhfopt.get_jk(dm, hermi, with_j, with_k)
 
 
-def patch(mf, device=0):
+def patch(mf, device=0, libpath=None):
     """Install the B200 builder as `mf.get_jk` on a PySCF SCF object (instance override).
 
     Keeps the reference semantics of SCF.get_jk (pyscf/scf/hf.py:2136-2160): one cached optimizer per
@@ -96,7 +96,8 @@ def patch(mf, device=0):
             dm = mf.make_rdm1()
         key = (id(mol), omega)
         if key not in opts:
-            opts[key] = VHFOpt(mol, direct_scf_tol=getattr(mf, 'direct_scf_tol', 1e-13), omega=omega, device=device)
+            opts[key] = VHFOpt(mol, direct_scf_tol=getattr(mf, 'direct_scf_tol', 1e-13), omega=omega, device=device,
+                               libpath=libpath)
         return opts[key].get_jk(dm, hermi, with_j, with_k)
 
     mf.get_jk = _get_jk

@@ -140,6 +140,39 @@ def test_reference_fingerprints_gpu():
     _check_reference_fingerprints(None)
 
 
+def test_patch_instance_override(emu_lib):
+    """jk.patch(mf) installs the builder as mf.get_jk, the instance-override hook PySCF documents
+    (examples/scf/43-custom_get_jk.py:36-45), with SCF.get_jk's defaults (mol=None -> mf.mol, dm=None -> mf.make_rdm1(),
+    one cached optimizer per omega; pyscf/scf/hf.py:2136-2160).  A stand-in object plays the SCF instance."""
+    from pyscf_b200 import jk
+
+    class FakeSCF:
+        def __init__(self, mol, dm):
+            self.mol, self._dm, self.direct_scf_tol = mol, dm, 1e-13
+
+        def make_rdm1(self):
+            return self._dm
+
+        def get_veff(self, mol=None, dm=None):          # what the reference's get_veff does with the hook
+            vj, vk = self.get_jk(mol, dm, 1)
+            return vj - vk * .5
+
+    mol = gto.M(atom=H2O, basis='6-31g')
+    dm = _sym(mol.nao, 2)
+    mf = jk.patch(FakeSCF(mol, dm), libpath=emu_lib)
+    rj, rk = O.get_jk(mol, dm)
+    vj, vk = mf.get_jk()
+    assert abs(vj - rj).max() < 1e-10 and abs(vk - rk).max() < 1e-10
+    assert abs(mf.get_veff() - (rj - .5 * rk)).max() < 1e-10
+    vj, vk = mf.get_jk(mol, dm, hermi=1, with_k=False)
+    assert vk is None and abs(vj - rj).max() < 1e-10
+    vklr = mf.get_jk(mol, dm, with_j=False, omega=0.4)[1]
+    assert abs(vklr - O.get_jk(mol, dm, omega=0.4)[1]).max() < 1e-10
+    assert len(mf._b200_opts) == 2                       # one optimizer per omega, reused on the next call
+    mf.get_jk(omega=0.4)
+    assert len(mf._b200_opts) == 2
+
+
 def test_incremental_veff_emulated(emu_lib):
     _check_incremental(emu_lib)
 
