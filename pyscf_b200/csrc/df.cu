@@ -1018,9 +1018,31 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
                     }
                     launches += 2;
 #else
+                    double* K = d->d_vk + (size_t)s * n2;
+                    if (use_occ) {
+                        // occupied-orbital path (tests only): Y_P = A_P C~ ; K += Y_P Y_P^T — the algebra of the tensor-core engine,
+                        // so that the host-side handling of mo_coeff / mo_occ is exercised on the CPU as well
+                        const double* Cm = d->d_occ + (size_t)s * nao * nocc;     // [nao][nocc]
+                        std::vector<double> Y((size_t)nao * nocc);
+                        for (int r = 0; r < nr; r++) {
+                            const double* A = d->d_A + (size_t)r * n2;
+                            for (int i = 0; i < nao; i++)
+                                for (int o = 0; o < nocc; o++) {
+                                    double acc = 0;
+                                    for (int j = 0; j < nao; j++) acc += A[(size_t)i * nao + j] * Cm[(size_t)j * nocc + o];
+                                    Y[(size_t)i * nocc + o] = acc;
+                                }
+                            for (int i = 0; i < nao; i++)
+                                for (int l = 0; l < nao; l++) {
+                                    double acc = 0;
+                                    for (int o = 0; o < nocc; o++) acc += Y[(size_t)i * nocc + o] * Y[(size_t)l * nocc + o];
+                                    K[(size_t)i * nao + l] += acc;
+                                }
+                        }
+                        continue;
+                    }
                     // K[i,l] += sum_P sum_jk A_P[i,j] D[j,k] A_P[k,l]   (tests only, O(N^4))
                     const double* D = d->d_dm + (size_t)s * n2;
-                    double* K = d->d_vk + (size_t)s * n2;
                     std::vector<double> T(n2);
                     for (int r = 0; r < nr; r++) {
                         const double* A = d->d_A + (size_t)r * n2;

@@ -214,20 +214,45 @@ class DF:
         shape = dm.shape
         dms = np.ascontiguousarray(dm.reshape(-1, nao, nao), dtype=np.float64)
         n_dm = len(dms)
-        occ = None
-        nocc = 0
-        # fast K path when the density carries its orbitals (pyscf/df/df_jk.py:339-357)
-        if with_k and mo_coeff is not None and mo_occ is not None and n_dm == 1:
-            mo_coeff = np.asarray(mo_coeff).reshape(nao, -1)
-            mo_occ = np.asarray(mo_occ).ravel()
-            mask = mo_occ > 0
-            occ = np.ascontiguousarray(mo_coeff[:, mask] * np.sqrt(mo_occ[mask]))[None]
-            nocc = occ.shape[-1]
+        h = self._handle
         vj = np.empty_like(dms) if with_j else None
         vk = np.empty_like(dms) if with_k else None
-        h = self._handle
-        h.check(h.lib.b200jk_df_jk(h._h, _lib.dptr(dms), n_dm, nao, _lib.dptr(occ), nocc, int(hermi), _lib.dptr(vj),
-                                   _lib.dptr(vk)), 'b200jk_df_jk')
+        # fast K path when the density carries its orbitals (pyscf/df/df_jk.py:339-357): one orbital set per density
+        # matrix; an ROHF-style tag (half as many orbital sets as densities) is expanded into (occupied, doubly occupied)
+        orbo = None
+        if with_k and mo_coeff is not None and mo_occ is not None:
+            mo_occ = np.asarray(mo_occ, dtype=np.float64)
+            nmo = mo_occ.shape[-1]
+            mo_coeff = np.asarray(mo_coeff, dtype=np.float64).reshape(-1, nao, nmo)
+            mo_occ = mo_occ.reshape(-1, nmo)
+            if mo_occ.shape[0] * 2 == n_dm and len(mo_coeff) * 2 == n_dm:          # ROHF density pair (df_jk.py:346-351)
+                mo_coeff = np.vstack((mo_coeff, mo_coeff))
+                occa = (mo_occ > 0).astype(np.float64)
+                occb = (mo_occ == 2).astype(np.float64)
+                if occa.sum() + occb.sum() != mo_occ.sum():
+                    raise RuntimeError('ROHF-style mo_occ must hold occupations 0, 1, 2')
+                mo_occ = np.vstack((occa, occb))
+            if len(mo_coeff) == n_dm and mo_occ.shape[0] == n_dm and (mo_occ >= 0).all():
+                orbo = [np.ascontiguousarray(mo_coeff[k][:, mo_occ[k] > 0] * np.sqrt(mo_occ[k][mo_occ[k] > 0])) for k in range(n_dm)]
+        if orbo is None or n_dm == 1:
+            occ = None if orbo is None else orbo[0][None]
+            nocc = 0 if orbo is None else orbo[0].shape[1]
+            if orbo is not None and nocc == 0:
+                occ = None      # no occupied orbital: K = 0 through the general path
+            h.check(h.lib.b200jk_df_jk(h._h, _lib.dptr(dms), n_dm, nao, _lib.dptr(occ), nocc, int(hermi), _lib.dptr(vj),
+                                       _lib.dptr(vk)), 'b200jk_df_jk')
+        else:
+            # several orbital sets (UHF, ROHF, state-averaged): J for all densities in one pass over the tensor, K set by set
+            # through the single-set occupied-orbital call (the tensor-core engine)
+            if with_j:
+                h.check(h.lib.b200jk_df_jk(h._h, _lib.dptr(dms), n_dm, nao, None, 0, int(hermi), _lib.dptr(vj), None), 'b200jk_df_jk')
+            for k in range(n_dm):
+                nocc = orbo[k].shape[1]
+                if nocc == 0:
+                    vk[k] = 0.0
+                    continue
+                h.check(h.lib.b200jk_df_jk(h._h, _lib.dptr(dms[k:k + 1]), 1, nao, _lib.dptr(orbo[k][None]), nocc, int(hermi), None,
+                                           _lib.dptr(vk[k:k + 1])), 'b200jk_df_jk')
         return (None if vj is None else vj.reshape(shape)), (None if vk is None else vk.reshape(shape))
 
     def stats(self):

@@ -73,6 +73,60 @@ def test_df_long_range_k_against_exact_4center(emu_lib):
     assert 1e-4 < abs(vk - ek).max() < 0.2 and abs(vj - ej).max() < 0.1   # fitting error of the full operator, for scale
 
 
+def _check_orbital_sets(libpath):
+    """Densities tagged with several orbital sets (UHF: one per spin; ROHF: one set, occupations 0/1/2 for an (alpha, beta)
+    density pair), pyscf/df/df_jk.py:339-357: J for all densities at once, K per set through the occupied-orbital engine;
+    must equal the general-density algebra."""
+    mol = gto.M(atom=H2O, basis='cc-pvdz')
+    nao = mol.nao
+    d = DF(mol, 'weigend', libpath=libpath).build()
+    ref, _ = O.cholesky_eri(mol, make_auxmol(mol, 'weigend'))
+    rng = np.random.RandomState(7)
+    ca = np.linalg.qr(rng.random_sample((nao, nao)))[0]
+    cb = np.linalg.qr(rng.random_sample((nao, nao)))[0]
+    occ_a = np.zeros(nao); occ_a[:5] = 1.0
+    occ_b = np.zeros(nao); occ_b[:4] = 1.0                    # different numbers of occupied orbitals per spin
+    dma = (ca * occ_a).dot(ca.T)
+    dmb = (cb * occ_b).dot(cb.T)
+    dms = np.array([dma, dmb])
+    vj, vk = d.get_jk(TaggedDM(dms, mo_coeff=np.array([ca, cb]), mo_occ=np.array([occ_a, occ_b])))
+    rj, rk = O.df_get_jk(ref, nao, dms)
+    assert vj.shape == dms.shape and abs(vj - rj).max() < 1e-9 and abs(vk - rk).max() < 1e-9
+    gj, gk = d.get_jk(dms)                                     # untagged: general-density path
+    assert abs(vj - gj).max() < 1e-10 and abs(vk - gk).max() < 1e-10
+    # ROHF: one orbital set with occupations 2,2,2,1,1,0,... for the (alpha, beta) densities
+    occ = np.zeros(nao); occ[:3] = 2.0; occ[3:5] = 1.0
+    da = (ca * (occ > 0)).dot(ca.T)
+    db = (ca * (occ == 2)).dot(ca.T)
+    pair = np.array([da, db])
+    vj, vk = d.get_jk(TaggedDM(pair, mo_coeff=ca, mo_occ=occ))
+    rj, rk = O.df_get_jk(ref, nao, pair)
+    assert abs(vj - rj).max() < 1e-9 and abs(vk - rk).max() < 1e-9
+    # fractional occupations scale the orbitals by sqrt(occ); a negative occupation falls back to the general path
+    occ_f = np.zeros(nao); occ_f[:4] = [2.0, 1.5, 0.5, 0.25]
+    df_ = (ca * occ_f).dot(ca.T)
+    assert abs(d.get_jk(TaggedDM(df_, mo_coeff=ca, mo_occ=occ_f))[1] - O.df_get_jk(ref, nao, df_)[1]).max() < 1e-9
+    occ_n = occ_f.copy(); occ_n[5] = -0.5
+    dn = (ca * occ_n).dot(ca.T)
+    assert abs(d.get_jk(TaggedDM(dn, mo_coeff=ca, mo_occ=occ_n))[1] - O.df_get_jk(ref, nao, dn)[1]).max() < 1e-9
+    # K only, and an empty orbital set
+    vj, vk = d.get_jk(TaggedDM(dms, mo_coeff=np.array([ca, cb]), mo_occ=np.array([occ_a, 0 * occ_b])), with_j=False)
+    assert vj is None and abs(vk[0] - rk0(ref, nao, dma)).max() < 1e-9 and abs(vk[1]).max() == 0
+
+
+def rk0(ref, nao, dm):
+    return O.df_get_jk(ref, nao, dm)[1]
+
+
+def test_orbital_sets_emulated(emu_lib):
+    _check_orbital_sets(emu_lib)
+
+
+@pytest.mark.gpu
+def test_orbital_sets_gpu():
+    _check_orbital_sets(None)
+
+
 def _check_assign_cderi(libpath, tmpdir):
     """mf.with_df._cderi = ndarray (pyscf/df/df.py:116-118; pyscf/df/test/test_df_jk.py:135-142 assigns an exact factorisation
     of the 4-center integrals and recovers the non-DF energy): a tensor made elsewhere is uploaded instead of built."""
