@@ -37,6 +37,12 @@ ref, _ = O.cholesky_eri(mol, make_auxmol(mol, 'weigend'))
 vj, vk = sd.get_jk(dm)
 rj, rk = O.df_get_jk(ref, nao, dm)
 assert abs(vj - rj).max() < 1e-10 and abs(vk - rk).max() < 1e-10
+# orbital-tagged density: the occupied-orbital K engine on every rank's rows (the emulation runs the same algebra)
+c = np.linalg.qr(np.random.random((nao, 5)))[0]
+dmo = TaggedDM(2 * c.dot(c.T), mo_coeff=c, mo_occ=np.full(5, 2.0))
+vjo, vko = sd.get_jk(dmo)
+rjo, rko = O.df_get_jk(ref, nao, np.asarray(dmo))
+assert abs(vjo - rjo).max() < 1e-10 and abs(vko - rko).max() < 1e-10
 # sharded BUILD: each rank builds only its rows of cderi
 dfs = DF(mol, 'weigend', libpath=emu, shard=(rank, dist.get_world_size())).build()
 assert dfs._cderi.shape[0] < ref.shape[0]
