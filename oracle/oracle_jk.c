@@ -225,3 +225,70 @@ void oracle_fill_int2c2e(double *out, int n, const int *loc, int sh0, int sh1, i
             free(b);
         }
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Timing / sampling wrapper around int2e_sph for bench.py's CPU arm (TEST INFRASTRUCTURE ONLY).
+ * The reference driver (CVHFnr_direct_drv, pyscf/lib/vhf/nr_direct.c:361-489) receives the integral function as a
+ * pointer (nr_direct.c:73); handing it this wrapper instead of int2e_sph
+ *   - accumulates, per OpenMP thread, the seconds spent inside the integral function (so the arm can report how much
+ *     of its time is the oracle's McMurchie-Davidson integrals and how much is reference driver/digestion code), and
+ *   - with stride m > 1 evaluates only every m-th surviving shell quartet of each thread (the others return 0 = "block
+ *     vanishes", which the driver skips like a libcint zero, nr_direct.c:73-76): a bounded sample of the same workload
+ *     whose time, multiplied by m, estimates the full build.
+ */
+#define ORACLE_MAXTHREADS 1024
+static double g_t_intor[ORACLE_MAXTHREADS * 8];
+static long g_n_calls[ORACLE_MAXTHREADS * 8], g_n_eval[ORACLE_MAXTHREADS * 8];
+static int g_stride = 1;
+
+void oracle_sample_reset(int stride)
+{
+    g_stride = stride < 1 ? 1 : stride;
+    memset(g_t_intor, 0, sizeof g_t_intor);
+    memset(g_n_calls, 0, sizeof g_n_calls);
+    memset(g_n_eval, 0, sizeof g_n_eval);
+}
+
+/* out[0] = summed thread-seconds inside the integral function, out[1] = calls, out[2] = calls evaluated */
+void oracle_sample_stats(double *out)
+{
+    double t = 0, c = 0, e = 0;
+    for (int i = 0; i < ORACLE_MAXTHREADS; i++) { t += g_t_intor[8 * i]; c += g_n_calls[8 * i]; e += g_n_eval[8 * i]; }
+    out[0] = t; out[1] = c; out[2] = e;
+}
+
+int oracle_omp_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+void oracle_omp_set_threads(int n)
+{
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#endif
+}
+
+int int2e_sph_sampled(double *out, int *dims, int *shls, int *atm, int natm, int *bas, int nbas, double *env, void *opt,
+                      double *cache)
+{
+    if (out == NULL) return int2e_sph(out, dims, shls, atm, natm, bas, nbas, env, opt, cache);
+#ifdef _OPENMP
+    int t = omp_get_thread_num() % ORACLE_MAXTHREADS;
+    double t0 = omp_get_wtime();
+#else
+    int t = 0;
+    double t0 = 0;
+#endif
+    long n = g_n_calls[8 * t]++;
+    if (g_stride > 1 && (n % g_stride) != 0) return 0;
+    int r = int2e_sph(out, dims, shls, atm, natm, bas, nbas, env, opt, cache);
+    g_n_eval[8 * t]++;
+#ifdef _OPENMP
+    g_t_intor[8 * t] += omp_get_wtime() - t0;
+#endif
+    return r;
+}

@@ -59,7 +59,7 @@ struct DFState {
     // J/K workspaces
     double *d_dmtril = nullptr, *d_rho = nullptr, *d_vjtril = nullptr, *d_A = nullptr, *d_Y = nullptr, *d_occ = nullptr,
            *d_dm = nullptr, *d_vk = nullptr, *d_vj = nullptr;
-    size_t ws_rows = 0, ws_nocc = 0, ws_ndm = 0;
+    size_t ws_rows = 0, ws_nocc = 0, ws_ndm = 0, ws_occ_ndm = 0;
     int k_mode = 1;      // 0: cuBLAS DGEMM (FP64 pipe), 1: tcgen05 int8 slices (i8gemm.cuh)
     int k_slices = 7;
     double* d_Y2 = nullptr; double* d_occT = nullptr; size_t y2_cap = 0, occT_cap = 0;
@@ -118,47 +118,37 @@ struct AuxC2SFn {
     }
 };
 
-// AO pair cart blocks -> packed spherical lower triangle: out[r][mu(mu+1)/2+nu]
-struct PairC2SFn {
-    const double* in; double* out; int64_t rowlen; long npair; int nsh;
-    const int64_t* pairoff;
-    const int *sph_sh, *sph_m, *sh_l, *c2s_off; const double* c2s;
+// AO pair cart blocks of ONE batch of shell pairs of one class -> packed spherical lower triangle out[r][mu(mu+1)/2+nu].
+// in: [nrow, cols] row-major, the Cartesian (a,b) block of pair p starts at column off[p] - col0, element X[b*nca + a].
+// One thread per (row, pair, m_a, m_b); every (mu >= nu) element of the packed row is produced by exactly one shell pair
+// (elements of shell pairs without surviving primitives are never written: the tensor is zero-filled beforehand).
+struct PairC2SBatchFn {
+    const double* in; double* out; int64_t cols, col0; long npair;
+    const ShellPair* pairs; const int64_t* off; int np; int la, lb;
+    const int *sh_sph, *c2s_off; const double* c2s;
     B2_HD void operator()(long idx) const
     {
-        long r = idx / npair;
-        long t = idx - r * npair;
-        long mu = (long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-        while ((mu + 1) * (mu + 2) / 2 <= t) mu++;
-        while (mu * (mu + 1) / 2 > t) mu--;
-        long nu = t - mu * (mu + 1) / 2;
-        int sa = sph_sh[mu], sb = sph_sh[nu];
-        int la = sh_l[sa], lb = sh_l[sb];
-        int nca = (la + 1) * (la + 2) / 2, ncb = (lb + 1) * (lb + 2) / 2;
-        const double* Ta = c2s + c2s_off[la] + sph_m[mu] * nca;
-        const double* Tb = c2s + c2s_off[lb] + sph_m[nu] * ncb;
+        const int nsa = 2 * la + 1, nsb = 2 * lb + 1, nca = (la + 1) * (la + 2) / 2, ncb = (lb + 1) * (lb + 2) / 2;
+        const long per_row = (long)np * nsa * nsb;
+        const long r = idx / per_row;
+        long e = idx - r * per_row;
+        const int p = (int)(e / (nsa * nsb));
+        e -= (long)p * nsa * nsb;
+        const int ma = (int)(e / nsb), mb = (int)(e - (long)ma * nsb);
+        const ShellPair& sp = pairs[p];
+        const long mu = sh_sph[sp.ish] + ma, nu = sh_sph[sp.jsh] + mb;
+        if (sp.ish == sp.jsh && mu < nu) return;
+        const double* Ta = c2s + c2s_off[la] + ma * nca;
+        const double* Tb = c2s + c2s_off[lb] + mb * ncb;
+        const double* X = in + r * cols + (off[p] - col0);
         double acc = 0.0;
-        if (sa >= sb) {
-            int64_t off = pairoff[(int64_t)sa * nsh + sb];
-            if (off >= 0) {
-                const double* X = in + r * rowlen + off;   // X[b*nca + a]
-                for (int b = 0; b < ncb; b++) {
-                    double tb = Tb[b];
-                    if (tb == 0.0) continue;
-                    for (int a = 0; a < nca; a++) acc += Ta[a] * tb * X[b * nca + a];
-                }
-            }
-        } else {
-            int64_t off = pairoff[(int64_t)sb * nsh + sa];
-            if (off >= 0) {
-                const double* X = in + r * rowlen + off;   // block of (sb, sa): X[a*ncb + b]
-                for (int a = 0; a < nca; a++) {
-                    double ta = Ta[a];
-                    if (ta == 0.0) continue;
-                    for (int b = 0; b < ncb; b++) acc += ta * Tb[b] * X[a * ncb + b];
-                }
-            }
+        for (int b = 0; b < ncb; b++) {
+            const double tb = Tb[b];
+            if (tb == 0.0) continue;
+            for (int a = 0; a < nca; a++) acc += Ta[a] * tb * X[b * nca + a];
         }
-        out[idx] = acc;
+        const long hi = mu >= nu ? mu : nu, lo = mu >= nu ? nu : mu;
+        out[r * npair + hi * (hi + 1) / 2 + lo] = acc;
     }
 };
 
@@ -373,7 +363,7 @@ static void for_each_j3c_batch(b200jk_handle h, DFState* d, double omega, stream
             }
             AuxC2SFn a2 {d_xc, d_xa, cols, nas, d->d_asph_sh, d->d_asph_m, d->d_ash_l, d->d_ash_cart, h->d_c2s_off, h->d_c2s};
             launch_1d((long)nas * cols, a2, st);
-            use(col0, cols, d_xa);
+            use(col0, cols, d_xa, cb, p0, p1);
             p0 = p1;
         }
     }
@@ -552,33 +542,40 @@ static int df_build_impl(b200jk_handle h, const int32_t* aux_atm, int aux_natm, 
         }
 #endif
 
-        // ---- (ij|P) in batches of AO shell pairs (bounded scratch): Cartesian rows -> spherical aux -> T . (P|ij)
+        // ---- (ij|P) in batches of AO shell pairs (bounded scratch): Cartesian rows -> spherical aux -> T . (P|ij) -> packed
+        //      spherical columns of this batch.  Nothing of size naux x (all Cartesian pairs) ever exists: the largest buffers are
+        //      the tensor itself and three batch-sized scratch arrays (<= ~3 GB each), so a 111 GB tensor fits one 180 GB GPU.
         const long npair = d->npair;
-        double* d_ycart = (double*)dev_alloc((size_t)std::max(nloc, 1) * d->rowlen * 8);
-        for_each_j3c_batch(h, d, omega, st, [&](int64_t col0, int64_t cols, const double* d_xa) {
+        const int64_t bcols = std::min<int64_t>(std::max<int64_t>(4096, (int64_t)((3ULL << 30) / ((size_t)d->naux_cart * 8))) + 128, d->rowlen);
+        double* d_ybatch = (double*)dev_alloc((size_t)std::max(nloc, 1) * (size_t)bcols * 8);
+        d->d_cderi = (double*)dev_alloc((size_t)std::max(nloc, 1) * npair * 8);
+        dev_zero(d->d_cderi, (size_t)std::max(nloc, 1) * npair * 8, st);
+        for_each_j3c_batch(h, d, omega, st, [&](int64_t col0, int64_t cols, const double* d_xa, int cb, int p0, int p1) {
             if (nloc <= 0) return;
+            if (cols > bcols) throw std::runtime_error("internal: 3-center batch larger than its scratch buffer");
 #ifndef B200JK_EMULATE
-            // row-major Y[nloc, cols] (ld rowlen) = T[nloc, nas] . Xa[nas, cols]  <=>  col-major Y^T = Xa^T . T^T
+            // row-major Y[nloc, cols] = T[nloc, nas] . Xa[nas, cols]  <=>  col-major Y^T = Xa^T . T^T
             const double one = 1.0, zero = 0.0;
             CKB(cublasDgemm(d->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)cols, nloc, nas, &one, d_xa, (int)cols, d_T, nas, &zero,
-                            d_ycart + col0, (int)d->rowlen));
+                            d_ybatch, (int)cols));
 #else
             for (int i = 0; i < nloc; i++)
                 for (int64_t c = 0; c < cols; c++) {
                     double acc = 0.0;
                     for (int k = 0; k < nas; k++) acc += d_T[(size_t)i * nas + k] * d_xa[(size_t)k * cols + c];
-                    d_ycart[(size_t)i * d->rowlen + col0 + c] = acc;
+                    d_ybatch[(size_t)i * cols + c] = acc;
                 }
 #endif
+            const int la = h->pc[cb].la, lb = h->pc[cb].lb;
+            PairC2SBatchFn p2{d_ybatch, d->d_cderi, cols, col0, npair, h->pc[cb].d_all + p0, d->d_ao_off[cb] + p0, p1 - p0, la, lb,
+                              h->d_sh_sph, h->d_c2s_off, h->d_c2s};
+            launch_1d((long)nloc * (p1 - p0) * (2 * la + 1) * (2 * lb + 1), p2, st);
         });
         dev_free(d_T);
-        d->d_cderi = (double*)dev_alloc((size_t)std::max(nloc, 1) * npair * 8);
-        PairC2SFn p2 {d_ycart, d->d_cderi, d->rowlen, npair, nsh, d->d_pairoff, h->d_sph_sh, h->d_sph_m, h->d_sh_l, h->d_c2s_off, h->d_c2s};
-        launch_1d((long)nloc * npair, p2, st);
+        dev_free(d_ybatch);
 #ifndef B200JK_EMULATE
         CK(cudaStreamSynchronize(st));
 #endif
-        dev_free(d_ycart);
         dev_free(d_j2c_cart);
     } catch (std::exception& e) { set_err(h, e.what()); return 2; }
     return 0;
@@ -665,7 +662,7 @@ extern "C" int b200jk_df_direct_j(b200jk_handle h, const double* dm, int n_dm, i
         }
         dev_zero(d_rho, (size_t)nas * n_dm * 8, st);
         // ---- pass 1: rho[s][P] = sum_col (P|col) Dc[s][col]
-        for_each_j3c_batch(h, d, d->omega, st, [&](int64_t col0, int64_t cols, const double* d_xa) {
+        for_each_j3c_batch(h, d, d->omega, st, [&](int64_t col0, int64_t cols, const double* d_xa, int, int, int) {
 #ifndef B200JK_EMULATE
             const double one = 1.0;
             CKB(cublasDgemm(d->cublas, CUBLAS_OP_T, CUBLAS_OP_N, nas, n_dm, (int)cols, &one, d_xa, (int)cols, d_dc + col0, (int)d->rowlen,
@@ -708,7 +705,7 @@ extern "C" int b200jk_df_direct_j(b200jk_handle h, const double* dm, int n_dm, i
 #endif
         // ---- pass 2: Jc[s][col] = sum_P (P|col) rho[s][P]
         double* d_jc = d_dc;   // reuse
-        for_each_j3c_batch(h, d, d->omega, st, [&](int64_t col0, int64_t cols, const double* d_xa) {
+        for_each_j3c_batch(h, d, d->omega, st, [&](int64_t col0, int64_t cols, const double* d_xa, int, int, int) {
 #ifndef B200JK_EMULATE
             const double one = 1.0, zero = 0.0;
             CKB(cublasDgemm(d->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)cols, n_dm, nas, &one, d_xa, (int)cols, d_rho, nas, &zero,
@@ -901,12 +898,12 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
         if (vk) {
             bool use_occ = (occ != nullptr && nocc > 0);
             int ncol = use_occ ? nocc : nao;
-            if ((size_t)kb > d->ws_rows || (size_t)ncol > d->ws_nocc) {
+            if ((size_t)kb > d->ws_rows || (size_t)ncol > d->ws_nocc || (size_t)n_dm > d->ws_occ_ndm) {
                 dev_free(d->d_A); dev_free(d->d_Y); dev_free(d->d_occ);
                 d->d_A = (double*)dev_alloc((size_t)kb * n2 * 8);
                 d->d_Y = (double*)dev_alloc((size_t)kb * ncol * nao * 8);
                 d->d_occ = (double*)dev_alloc((size_t)n_dm * nao * ncol * 8);
-                d->ws_rows = kb; d->ws_nocc = ncol;
+                d->ws_rows = kb; d->ws_nocc = ncol; d->ws_occ_ndm = n_dm;
             }
             if (use_occ) {
                 if (!on_device) h2d(d->d_occ, occ, (size_t)n_dm * nao * nocc * 8, st);

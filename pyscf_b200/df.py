@@ -51,15 +51,24 @@ class DF:
         atm = np.ascontiguousarray(aux._atm, dtype=np.int32)
         bas = np.ascontiguousarray(aux._bas, dtype=np.int32)
         env = np.ascontiguousarray(aux._env, dtype=np.float64)
-        omega = 0.0 if self.omega is None else float(self.omega)
+        omega = self._effective_omega()
         if self.shard is not None:
             h.check(h.lib.b200jk_set_shard(h._h, int(self.shard[0]), int(self.shard[1])), 'b200jk_set_shard')
+        self._built_omega = omega
         h.check(h.lib.b200jk_df_build(h._h, _lib.iptr(atm), len(atm), _lib.iptr(bas), len(bas), _lib.dptr(env), len(env),
                                       omega, self.lindep), 'b200jk_df_build')
         self._handle = h
         self.nao = int(mol.ao_loc_nr(cart=False)[-1])
         self.set_k_engine(self.k_engine, self.k_slices)
         return self
+
+    def _effective_omega(self):
+        """Operator of the tensor: self.omega when set (range_coulomb children), else what the molecule carries in
+        env[PTR_RANGE_OMEGA] — mol.omega or an enclosing `with mol.with_range_coulomb(w)`, as the reference's integral calls see
+        it (pyscf/df/incore.py:129-220 runs under the molecule's environment)."""
+        if self.omega is not None:
+            return float(self.omega)
+        return float(self.mol._env[8])
 
     def _build_from_cderi(self):
         """Upload an assigned tensor (mf.with_df._cderi = ndarray | 'file.npy'; pyscf/df/df.py:116-118,
@@ -104,9 +113,12 @@ class DF:
             self._handle.close()
         if getattr(self, '_vjopt', None) is not None:
             self._vjopt.close()
+        for child in self._rsh_df.values():
+            child.reset()
         self._handle = None
         self._vjopt = None
         self._rsh_df = {}
+        self._built_omega = None
         return self
 
     def get_naoaux(self):
@@ -168,7 +180,8 @@ class DF:
         atm = np.ascontiguousarray(aux._atm, dtype=np.int32)
         bas = np.ascontiguousarray(aux._bas, dtype=np.int32)
         env = np.ascontiguousarray(aux._env, dtype=np.float64)
-        omega = 0.0 if self.omega is None else float(self.omega)
+        omega = self._effective_omega()
+        self._built_omega = omega
         h.check(h.lib.b200jk_df_prepare_j(h._h, _lib.iptr(atm), len(atm), _lib.iptr(bas), len(bas), _lib.dptr(env),
                                           len(env), omega, self.lindep), 'b200jk_df_prepare_j')
         self._vjopt = h
@@ -194,8 +207,12 @@ class DF:
         return vj.reshape(shape)
 
     def get_jk(self, dm, hermi=1, with_j=True, with_k=True, direct_scf_tol=1e-13, omega=None):
-        if omega is not None and omega != 0 and omega != self.omega:
+        if omega is not None and float(omega) != self._effective_omega():
+            # pyscf/df/df.py:259-296: a different operator lives on its own cached DF object (omega = 0: the plain Coulomb one)
             return self.range_coulomb(omega).get_jk(dm, hermi, with_j, with_k, direct_scf_tol)
+        if self._cderi_in is None and (self._handle is not None or self._vjopt is not None) and \
+                getattr(self, '_built_omega', None) not in (None, self._effective_omega()):
+            self.reset()       # the molecule's own operator changed since the tensor was built (mol.omega, with_range_coulomb)
         if not with_k and self._handle is None and self.shard is None and self._cderi_in is None:
             # J only and no tensor yet: integral-direct J (pyscf/df/df_jk.py:282-285)
             return self.get_j(dm, hermi, direct_scf_tol), None
@@ -264,7 +281,13 @@ class DF:
 
 
 class TaggedDM(np.ndarray):
-    """ndarray carrying mo_coeff / mo_occ like lib.tag_array (pyscf/lib/numpy_helper.py; hf.py:868)."""
+    """ndarray carrying mo_coeff / mo_occ like lib.tag_array (pyscf/lib/numpy_helper.py:1460-1500; hf.py:868).
+
+    As in the reference the tags describe THIS array's contents only: any ufunc result (dm - dm_last, 0.5 * dm, ...) comes
+    back as a plain ndarray (`__array_wrap__`, numpy_helper.py:1477-1484) and views / slices start without tags, so a derived
+    density can never reach the occupied-orbital K path with stale orbitals."""
+    mo_coeff = None
+    mo_occ = None
 
     def __new__(cls, a, mo_coeff=None, mo_occ=None):
         obj = np.asarray(a).view(cls)
@@ -272,18 +295,97 @@ class TaggedDM(np.ndarray):
         obj.mo_occ = mo_occ
         return obj
 
-    def __array_finalize__(self, obj):
-        self.mo_coeff = getattr(obj, 'mo_coeff', None)
-        self.mo_occ = getattr(obj, 'mo_occ', None)
+    def __array_wrap__(self, out, context=None, return_scalar=False):
+        if out.ndim == 0:
+            return out[()]
+        return out.view(np.ndarray)
+
+    def __reduce__(self):
+        pickled = np.ndarray.__reduce__(self)
+        return (pickled[0], pickled[1], pickled[2] + ((self.mo_coeff, self.mo_occ),))
+
+    def __setstate__(self, state):
+        np.ndarray.__setstate__(self, state[:-1])
+        self.mo_coeff, self.mo_occ = state[-1]
 
 
-def density_fit(mf, auxbasis=None, device=0, only_dfj=False):
-    """Install a B200 DF object as mf.with_df (pyscf/df/df_jk.py:31-107 does the same with df.DF).  With
-    only_dfj=True J comes from the fitted tensor and K from the 4-center kernels (RIJONX; _DFHF.get_jk,
-    pyscf/df/df_jk.py:150-179)."""
-    mf.with_df = DF(mf.mol, auxbasis, device=device)
-    mf.only_dfj = only_dfj
-    return mf
+def tag_array(a, **kwargs):
+    """lib.tag_array (pyscf/lib/numpy_helper.py:1487-1500)."""
+    t = TaggedDM(a, getattr(a, 'mo_coeff', None), getattr(a, 'mo_occ', None))
+    for k, v in kwargs.items():
+        setattr(t, k, v)
+    return t
+
+
+class _DFHF:
+    """Mixin placed in front of the mean-field class by density_fit(), the role of df_jk._DFHF (pyscf/df/df_jk.py:104-179):
+    get_jk goes to with_df; only_dfj routes K to the exact 4-center builder; direct_scf := only_dfj; reset() resets with_df."""
+    only_dfj = None
+
+    def reset(self, mol=None):
+        if self.with_df is not None:
+            self.with_df.reset(mol)
+        vh = getattr(self, '_b200_direct_jk', None)
+        if vh is not None and hasattr(vh, '_cache'):
+            vh._cache.clear()
+        return super().reset(mol)
+
+    def get_jk(self, mol=None, dm=None, hermi=1, with_j=True, with_k=True, omega=None):
+        assert with_j or with_k
+        if mol is None:
+            mol = self.mol
+        if dm is None:
+            dm = self.make_rdm1()
+        if not self.with_df:       # mf.with_df = None switches density fitting off (df_jk.py:153-154)
+            return self._exact_get_jk(mol, dm, hermi, with_j, with_k, omega)
+        vj = vk = None
+        with_dfk = with_k and not self.only_dfj
+        if with_j or with_dfk:
+            vj, vk = self.with_df.get_jk(dm, hermi, with_j, with_dfk, getattr(self, 'direct_scf_tol', 1e-13), omega)
+        if with_k and not with_dfk:
+            vk = self._exact_get_jk(mol, dm, hermi, False, True, omega)[1]
+        return vj, vk
+
+    def _exact_get_jk(self, mol, dm, hermi, with_j, with_k, omega):
+        """super().get_jk of the reference: the B200 4-center builder when jk.patch() was applied to the object before (its
+        instance override is kept as _b200_direct_jk), else the mean-field class's own get_jk."""
+        f = getattr(self, '_b200_direct_jk', None)
+        if f is not None:
+            return f(mol, dm, hermi, with_j, with_k, omega)
+        return super().get_jk(mol, dm, hermi, with_j, with_k, omega)
+
+
+def density_fit(mf, auxbasis=None, with_df=None, only_dfj=False, device=0):
+    """df_jk.density_fit (pyscf/df/df_jk.py:31-102) with a B200 DF object: returns an object of the dynamic class
+    (_DFHF, mf.__class__) sharing mf's attributes, whose get_jk is served by with_df.get_jk (J and K from the fitted tensor) or,
+    with only_dfj=True, J from the tensor and K from the exact 4-center path (RIJONX, df_jk.py:157-179).  An object that is
+    already density-fitted just gets the new with_df / only_dfj (df_jk.py:88-99)."""
+    if with_df is None:
+        with_df = DF(mf.mol, auxbasis, device=device)
+        with_df.verbose = getattr(mf, 'verbose', 0)
+        with_df.stdout = getattr(mf, 'stdout', None)
+        with_df.max_memory = getattr(mf, 'max_memory', 4000)
+    if isinstance(mf, _DFHF):
+        mf.with_df = with_df
+        mf.only_dfj = only_dfj
+        mf.direct_scf = only_dfj
+        return mf
+    base = mf.__class__
+    cls = type('DF' + base.__name__, (_DFHF, base), {})
+    dfmf = object.__new__(cls)
+    dfmf.__dict__.update(mf.__dict__)
+    # an instance-level get_jk (jk.patch) would shadow the class method: keep it as the exact builder instead
+    inst = dfmf.__dict__.pop('get_jk', None)
+    if inst is not None:
+        dfmf._b200_direct_jk = inst
+    dfmf.__dict__.pop('reset', None)      # jk.patch's reset wrapper: _DFHF.reset clears the same cache
+    if inst is not None and getattr(mf, '_b200_opts', None) is not None:
+        inst._cache = mf._b200_opts
+    dfmf._eri = None
+    dfmf.with_df = with_df
+    dfmf.only_dfj = only_dfj
+    dfmf.direct_scf = only_dfj     # df_jk.py:133-137: incremental direct-SCF K only when K is the exact one
+    return dfmf
 
 
 def get_jk_only_dfj(with_df, mol, dm, hermi=1, with_j=True, with_k=True, omega=None, direct_scf_tol=1e-13, vhfopt=None):

@@ -186,9 +186,11 @@ class Mole:
 
     @contextlib.contextmanager
     def with_range_coulomb(self, omega):
-        """pyscf/gto/mole.py:2940-2951: omega>0 erf(w r)/r, omega<0 erfc, 0/None full Coulomb."""
+        """pyscf/gto/mole.py:2940-2951, 3049-3063: omega>0 erf(w r)/r, omega<0 erfc, 0 full Coulomb; None leaves the
+        operator the molecule already carries (mol.omega / an enclosing context) untouched."""
         old = self._env[PTR_RANGE_OMEGA]
-        self._env[PTR_RANGE_OMEGA] = 0.0 if omega is None else omega
+        if omega is not None:
+            self._env[PTR_RANGE_OMEGA] = omega
         try:
             yield self
         finally:

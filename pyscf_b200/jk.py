@@ -8,9 +8,35 @@ Mirrors (same names, argument meaning, shapes and error behaviour):
 Install on a PySCF mean-field object with `patch(mf)` (instance override of get_jk, the hook
 documented in examples/scf/43-custom_get_jk.py:36-45).
 """
+import hashlib
+import weakref
+
 import numpy as np
 
 from . import lib as _lib
+
+PTR_RANGE_OMEGA = 8      # pyscf/gto/mole.py:80
+
+
+def effective_omega(mol, omega):
+    """The operator a call with `omega` sees (pyscf/scf/hf.py:1021 `with mol.with_range_coulomb(omega)`, pyscf/gto/mole.py:2940-2951,
+    3049-3063): an explicit omega wins; None means whatever the molecule already carries in env[PTR_RANGE_OMEGA] (mol.omega or an
+    enclosing `with mol.with_range_coulomb(w)`)."""
+    if omega is None:
+        return float(mol._env[PTR_RANGE_OMEGA])
+    return float(omega)
+
+
+def mol_fingerprint(mol):
+    """Identity of the integral tables (geometry, basis): cached optimizers are only reused for identical _atm/_bas/_env
+    (everything but the range-separation slot, which is part of the cache key)."""
+    env = np.array(mol._env, dtype=np.float64, copy=True)
+    env[PTR_RANGE_OMEGA] = 0.0
+    hsh = hashlib.sha1()
+    hsh.update(np.ascontiguousarray(mol._atm, dtype=np.int32).tobytes())
+    hsh.update(np.ascontiguousarray(mol._bas, dtype=np.int32).tobytes())
+    hsh.update(env.tobytes())
+    return hsh.hexdigest()
 
 
 class VHFOpt:
@@ -19,12 +45,13 @@ class VHFOpt:
     def __init__(self, mol, direct_scf_tol=1e-13, omega=None, device=0, libpath=None):
         self.mol = mol
         self.direct_scf_tol = direct_scf_tol
-        self.omega = 0.0 if omega is None else float(omega)
+        self.omega = effective_omega(mol, omega)
+        self.fingerprint = mol_fingerprint(mol)
+        if getattr(mol, 'cart', False):
+            raise NotImplementedError('cart=True molecules are not supported')
         env = np.array(mol._env, dtype=np.float64, copy=True)
         self.handle = _lib.Handle(mol._atm, mol._bas, env, device=device, libpath=libpath)
         self.nao = int(mol.ao_loc_nr(cart=False)[-1]) if hasattr(mol, 'ao_loc_nr') else mol.nao
-        if getattr(mol, 'cart', False):
-            raise NotImplementedError('cart=True molecules are not supported')
         h = self.handle
         h.check(h.lib.b200jk_set_screening(h._h, direct_scf_tol, self.omega), 'b200jk_set_screening')
 
@@ -39,8 +66,8 @@ class VHFOpt:
     def get_jk(self, dm, hermi=1, with_j=True, with_k=True):
         dm = np.asarray(dm)
         if np.iscomplexobj(dm):
-            # pyscf/scf/hf.py:1017-1031: real and imaginary parts are contracted separately
-            vjr, vkr = self.get_jk(dm.real, 0 if hermi else 0, with_j, with_k)
+            # pyscf/scf/hf.py:1017-1031: real and imaginary parts are contracted separately, without symmetry
+            vjr, vkr = self.get_jk(dm.real, 0, with_j, with_k)
             vji, vki = self.get_jk(dm.imag, 0, with_j, with_k)
             vj = None if vjr is None else vjr + 1j * vji
             vk = None if vkr is None else vkr + 1j * vki
@@ -69,37 +96,86 @@ class VHFOpt:
         self.handle.close()
 
 
-_opt_cache = {}
+class _OptCache:
+    """Optimizers per (molecule tables, effective omega), like SCF._opt[omega] (pyscf/scf/hf.py:1803,2141-2146).  Entries hang on
+    the molecule OBJECT through a weak reference (a dead molecule frees its GPU handles; a recycled id() can never hit a stale
+    entry) and are validated against a fingerprint of _atm/_bas/_env, so an in-place mol.build() / set_geom_() gets a fresh one."""
+
+    def __init__(self, max_entries=8):
+        self.max_entries = max_entries
+        self._d = {}     # id(mol) -> (weakref | None, {omega: VHFOpt})
+
+    def _drop(self, key):
+        ent = self._d.pop(key, None)
+        if ent:
+            for o in ent[1].values():
+                o.close()
+
+    def get(self, mol, omega, **kw):
+        key = id(mol)
+        ent = self._d.get(key)
+        if ent is not None and ent[0] is not None and ent[0]() is not mol:
+            self._drop(key)
+            ent = None
+        if ent is None:
+            try:
+                ref = weakref.ref(mol, lambda _r, k=key: self._drop(k))
+            except TypeError:
+                ref = None
+            while len(self._d) >= self.max_entries:
+                self._drop(next(iter(self._d)))
+            ent = self._d[key] = (ref, {})
+        om = effective_omega(mol, omega)
+        opt = ent[1].get(om)
+        if opt is not None and (opt.fingerprint != mol_fingerprint(mol) or (ent[0] is None and opt.mol is not mol)):
+            opt.close()
+            opt = None
+        if opt is None:
+            opt = ent[1][om] = VHFOpt(mol, omega=omega, **kw)
+        return opt
+
+    def clear(self):
+        for key in list(self._d):
+            self._drop(key)
+
+    def __len__(self):
+        return sum(len(ent[1]) for ent in self._d.values())
+
+
+_opt_cache = _OptCache()
 
 
 def get_jk(mol, dm, hermi=1, vhfopt=None, with_j=True, with_k=True, omega=None):
     """Drop-in for pyscf.scf.hf.get_jk (pyscf/scf/hf.py:963): returns (vj, vk) shaped like dm."""
     if vhfopt is None:
-        key = (id(mol), omega)
-        vhfopt = _opt_cache.get(key)
-        if vhfopt is None or vhfopt.mol is not mol:
-            vhfopt = _opt_cache[key] = VHFOpt(mol, omega=omega)
+        vhfopt = _opt_cache.get(mol, omega)
     return vhfopt.get_jk(dm, hermi, with_j, with_k)
 
 
 def patch(mf, device=0, libpath=None):
     """Install the B200 builder as `mf.get_jk` on a PySCF SCF object (instance override).
 
-    Keeps the reference semantics of SCF.get_jk (pyscf/scf/hf.py:2136-2160): one cached optimizer per
-    omega in mf._opt, rebuilt after mf.reset()."""
-    opts = {}
+    Keeps the reference semantics of SCF.get_jk (pyscf/scf/hf.py:2136-2160): one cached optimizer per omega (mf._opt there,
+    mf._b200_opts here), dropped by mf.reset() (pyscf/scf/hf.py:2331: reset clears _opt) and rebuilt when the molecule's
+    integral tables change."""
+    cache = _OptCache()
 
     def _get_jk(mol=None, dm=None, hermi=1, with_j=True, with_k=True, omega=None):
         if mol is None:
             mol = mf.mol
         if dm is None:
             dm = mf.make_rdm1()
-        key = (id(mol), omega)
-        if key not in opts:
-            opts[key] = VHFOpt(mol, direct_scf_tol=getattr(mf, 'direct_scf_tol', 1e-13), omega=omega, device=device,
-                               libpath=libpath)
-        return opts[key].get_jk(dm, hermi, with_j, with_k)
+        opt = cache.get(mol, omega, direct_scf_tol=getattr(mf, 'direct_scf_tol', 1e-13), device=device, libpath=libpath)
+        return opt.get_jk(dm, hermi, with_j, with_k)
 
+    _get_jk._b200_direct = True
     mf.get_jk = _get_jk
-    mf._b200_opts = opts
+    mf._b200_opts = cache
+    cls_reset = getattr(mf, 'reset', None)
+    if cls_reset is not None and not getattr(cls_reset, '_b200_wrapped', False):
+        def _reset(mol=None):
+            cache.clear()
+            return cls_reset(mol)
+        _reset._b200_wrapped = True
+        mf.reset = _reset
     return mf

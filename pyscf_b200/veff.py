@@ -36,9 +36,12 @@ class TaggedArray(np.ndarray):
         obj.__dict__.update(tags)
         return obj
 
-    def __array_finalize__(self, obj):
-        if obj is not None and hasattr(obj, '__dict__'):
-            self.__dict__.update(obj.__dict__)
+    # tags (ecoul, vj, vk) describe this array only: results of arithmetic come back untagged, as lib.tag_array's
+    # NPArrayWithTag.__array_wrap__ does (pyscf/lib/numpy_helper.py:1477-1484)
+    def __array_wrap__(self, out, context=None, return_scalar=False):
+        if out.ndim == 0:
+            return out[()]
+        return out.view(np.ndarray)
 
 
 def tag_array(a, **tags):

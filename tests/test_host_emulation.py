@@ -172,3 +172,171 @@ def test_emulated_experimental_layouts(emu_lib, emu_lib_experimental):
         a = VHFOpt(mol, omega=omega, libpath=emu_lib_experimental).get_jk(d, hermi=1)
         r = O.get_jk(mol, d, omega=omega)
         assert abs(a[0] - r[0]).max() < 1e-10 and abs(a[1] - r[1]).max() < 1e-10
+
+
+# ---- boundary semantics: tags, density_fit routing, range-separation from the molecule, cache lifetime
+def test_tags_expire_on_arithmetic():
+    """lib.tag_array semantics (pyscf/lib/numpy_helper.py:1477-1484): ufunc results and slices carry no orbital tags."""
+    from pyscf_b200.df import TaggedDM
+    from pyscf_b200.veff import tag_array
+    c = np.random.RandomState(0).standard_normal((6, 2))
+    dm = TaggedDM(2 * c.dot(c.T), mo_coeff=c, mo_occ=np.array([2.0, 2.0]))
+    assert dm.mo_coeff is c
+    for derived in (dm - 0.5 * dm, dm * 0.5, dm + dm, -dm, dm[:3], np.asarray(dm) * 1.0):
+        assert getattr(derived, 'mo_coeff', None) is None and getattr(derived, 'mo_occ', None) is None
+    assert type(dm - dm) is np.ndarray
+    v = tag_array(np.eye(3), ecoul=1.5)
+    assert v.ecoul == 1.5 and not hasattr(v * 2.0, 'ecoul')
+
+
+def test_df_get_jk_ignores_stale_tags(emu_lib):
+    """DF.get_jk(tagged - other) must equal the untagged result (the stale orbitals are not used)."""
+    from pyscf_b200.df import DF, TaggedDM
+    mol = gto.M(atom='O 0 0 0; H 0 -0.757 0.587; H 0 0.757 0.587', basis='sto-3g')
+    nao = mol.nao
+    rng = np.random.RandomState(3)
+    c = np.linalg.qr(rng.standard_normal((nao, 3)))[0]
+    dm = TaggedDM(2 * c.dot(c.T), mo_coeff=c, mo_occ=np.full(3, 2.0))
+    other = rng.standard_normal((nao, nao))
+    other = other + other.T
+    d = DF(mol, 'weigend', libpath=emu_lib).build()
+    vj1, vk1 = d.get_jk(dm - other)
+    vj2, vk2 = d.get_jk(np.asarray(dm) - other)
+    assert abs(vj1 - vj2).max() < 1e-12 and abs(vk1 - vk2).max() < 1e-12
+    vk_tag = d.get_jk(dm)[1]
+    assert abs(vk_tag - d.get_jk(np.asarray(dm))[1]).max() < 1e-10   # occupied-orbital path == general path on the tagged density
+
+
+class _StandInSCF:
+    """Minimal stand-in for pyscf.scf.hf.SCF with the reference's call order: get_veff -> get_jk(mol, dm, hermi), get_j/get_k
+    funnel into get_jk (pyscf/scf/hf.py:2161-2201); reset(mol) (hf.py:2331)."""
+    direct_scf = True
+    direct_scf_tol = 1e-13
+
+    def __init__(self, mol):
+        self.mol = mol
+        self.calls = []
+        self._eri = 'incore'
+        self.nreset = 0
+
+    def make_rdm1(self):
+        return np.eye(self.mol.nao)
+
+    def get_jk(self, mol=None, dm=None, hermi=1, with_j=True, with_k=True, omega=None):
+        self.calls.append(('exact', with_j, with_k, omega))
+        n = self.mol.nao
+        return (np.full((n, n), 1.0) if with_j else None), (np.full((n, n), 2.0) if with_k else None)
+
+    def get_j(self, mol=None, dm=None, hermi=1, omega=None):
+        return self.get_jk(mol, dm, hermi, with_k=False, omega=omega)[0]
+
+    def get_k(self, mol=None, dm=None, hermi=1, omega=None):
+        return self.get_jk(mol, dm, hermi, with_j=False, omega=omega)[1]
+
+    def get_veff(self, mol=None, dm=None):
+        vj, vk = self.get_jk(mol, dm, 1)
+        return vj - 0.5 * vk
+
+    def reset(self, mol=None):
+        self.nreset += 1
+        if mol is not None:
+            self.mol = mol
+        return self
+
+
+class _FakeDF:
+    def __init__(self):
+        self.calls = []
+        self.nreset = 0
+
+    def get_jk(self, dm, hermi=1, with_j=True, with_k=True, direct_scf_tol=1e-13, omega=None):
+        self.calls.append((with_j, with_k, omega))
+        n = np.asarray(dm).shape[-1]
+        return (np.full((n, n), 10.0) if with_j else None), (np.full((n, n), 20.0) if with_k else None)
+
+    def reset(self, mol=None):
+        self.nreset += 1
+
+
+def test_density_fit_routes_like_dfhf():
+    """density_fit(mf) returns a (_DFHF, mf.__class__) object whose get_jk is served by with_df (pyscf/df/df_jk.py:104-179)."""
+    from pyscf_b200.df import density_fit, _DFHF
+    mol = gto.M(atom='O 0 0 0; H 0 -0.757 0.587; H 0 0.757 0.587', basis='sto-3g')
+    mf = _StandInSCF(mol)
+    fake = _FakeDF()
+    dfmf = density_fit(mf, with_df=fake)
+    assert isinstance(dfmf, _DFHF) and isinstance(dfmf, _StandInSCF) and type(dfmf).__name__ == 'DF_StandInSCF'
+    assert dfmf._eri is None and not dfmf.direct_scf and dfmf.with_df is fake
+    dm = np.eye(mol.nao)
+    vj, vk = dfmf.get_jk(mol, dm)
+    assert vj[0, 0] == 10.0 and vk[0, 0] == 20.0 and fake.calls[-1] == (True, True, None)
+    assert dfmf.get_veff(mol, dm)[0, 0] == 0.0                         # get_veff funnels into the DF get_jk
+    assert dfmf.get_k(mol, dm, omega=0.3)[0, 0] == 20.0 and fake.calls[-1] == (False, True, 0.3)
+    # only_dfj: J fitted, K from the class's exact get_jk; direct_scf switched back on (df_jk.py:133-137,157-179)
+    dfmf2 = density_fit(mf, with_df=fake, only_dfj=True)
+    vj, vk = dfmf2.get_jk(mol, dm)
+    assert vj[0, 0] == 10.0 and vk[0, 0] == 2.0 and dfmf2.direct_scf
+    assert fake.calls[-1] == (True, False, None) and dfmf2.calls[-1] == ('exact', False, True, None)
+    # with_df = None switches density fitting off (df_jk.py:153-154)
+    dfmf.with_df = None
+    assert dfmf.get_jk(mol, dm)[0][0, 0] == 1.0
+    dfmf.with_df = fake
+    dfmf.reset()
+    assert fake.nreset == 1 and dfmf.nreset == 1
+    # an object patched with jk.patch keeps the B200 4-center builder as its exact path
+    marker = []
+
+    def inst_get_jk(mol=None, dm=None, hermi=1, with_j=True, with_k=True, omega=None):
+        marker.append((with_j, with_k))
+        return None, np.full((mol.nao, mol.nao), 7.0)
+    mf2 = _StandInSCF(mol)
+    mf2.get_jk = inst_get_jk
+    dfmf3 = density_fit(mf2, with_df=fake, only_dfj=True)
+    assert dfmf3.get_jk(mol, dm)[1][0, 0] == 7.0 and marker == [(False, True)]
+
+
+def test_omega_none_uses_the_molecules_operator(emu_lib):
+    """omega=None means the molecule's own range separation (pyscf/scf/hf.py:1021, pyscf/gto/mole.py:2940-2951)."""
+    from pyscf_b200 import jk as JK
+    from pyscf_b200.df import DF
+    mol = gto.M(atom='O 0 0 0; H 0 -0.757 0.587; H 0 0.757 0.587', basis='sto-3g')
+    np.random.seed(2)
+    dm = np.random.random((mol.nao,) * 2)
+    dm = dm + dm.T
+    full = JK.VHFOpt(mol, libpath=emu_lib).get_jk(dm)
+    lr = JK.VHFOpt(mol, omega=0.3, libpath=emu_lib).get_jk(dm)
+    assert abs(full[1] - lr[1]).max() > 1e-3
+    with mol.with_range_coulomb(0.3):
+        inside = JK.VHFOpt(mol, libpath=emu_lib).get_jk(dm)
+        assert JK.effective_omega(mol, None) == 0.3 and JK.effective_omega(mol, 0.0) == 0.0
+        d_in = DF(mol, 'weigend', libpath=emu_lib)
+        kin = d_in.get_jk(dm)[1]
+    assert abs(inside[0] - lr[0]).max() < 1e-12 and abs(inside[1] - lr[1]).max() < 1e-12
+    assert JK.effective_omega(mol, None) == 0.0
+    kfull = DF(mol, 'weigend', libpath=emu_lib).get_jk(dm)[1]
+    klr = DF(mol, 'weigend', libpath=emu_lib).get_jk(dm, omega=0.3)[1]
+    assert abs(kin - klr).max() < 1e-12 and abs(kin - kfull).max() > 1e-3
+    # a tensor built for one operator is not reused when the molecule's operator changes
+    d = DF(mol, 'weigend', libpath=emu_lib)
+    k0 = d.get_jk(dm)[1]
+    with mol.with_range_coulomb(0.3):
+        k1 = d.get_jk(dm)[1]
+    assert abs(k0 - kfull).max() < 1e-12 and abs(k1 - klr).max() < 1e-12
+
+
+def test_patch_cache_follows_the_molecule(emu_lib):
+    """jk.patch: optimizers are dropped by mf.reset() and rebuilt when the molecule's tables change in place."""
+    from pyscf_b200 import jk as JK
+    mol = gto.M(atom='O 0 0 0; H 0 -0.757 0.587; H 0 0.757 0.587', basis='sto-3g')
+    mf = JK.patch(_StandInSCF(mol), libpath=emu_lib)
+    dm = np.eye(mol.nao)
+    k0 = mf.get_jk(mol, dm)[1]
+    opt0 = mf._b200_opts.get(mol, None, libpath=emu_lib)
+    assert mf._b200_opts.get(mol, None, libpath=emu_lib) is opt0          # cached
+    mol._env[mol._atm[1, 1] + 2] += 0.2                               # move an atom in place (set_geom_-like)
+    k1 = mf.get_jk(mol, dm)[1]
+    assert abs(k1 - k0).max() > 1e-4 and mf._b200_opts.get(mol, None, libpath=emu_lib) is not opt0
+    mf.reset()
+    assert mf.nreset == 1 and not mf._b200_opts._d
+    # the module-level cache is bounded and keyed on live objects
+    JK._opt_cache.clear()
