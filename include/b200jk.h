@@ -108,6 +108,10 @@ int b200jk_df_set_cderi(b200jk_handle h, const double* cderi, int naux, int nao)
  * (pyscf/df/incore.py:134-136; what DF.loop() yields, pyscf/df/df.py:214-242). */
 int b200jk_df_get_cderi(b200jk_handle h, double* out, int r0, int nr);
 
+/* Columns cols[ncols] (packed AO-pair indices mu(mu+1)/2+nu, mu >= nu) of all LOCAL rows: out[nrow_local][ncols] — numpy
+ * slicing dfobj._cderi[:, cols] on the reference's ndarray tensor (pyscf/df/df.py:116); samples a tensor too large to copy. */
+int b200jk_df_get_cderi_cols(b200jk_handle h, double* out, const int64_t* cols, int ncols);
+
 /* Schwarz table q_cond[nbas,nbas] in the reference's (contracted, spherical-order) shell indexing. */
 int b200jk_get_q_cond(b200jk_handle h, double* q_cond, int nbas);
 

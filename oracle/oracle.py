@@ -120,6 +120,26 @@ def int3c2e(mol, auxmol):
     return out
 
 
+def int3c2e_pairs(mol, auxmol, pairs):
+    """(ij|P) for a list of AO shell pairs [(ish, jsh), ...]: returns (out[naux, ncol], col0[npair]); pair p owns the
+    columns col0[p] + a*dj + b (a, b = functions of shells ish, jsh).  Operator from mol._env[8]."""
+    atm, bas, env = conc_mol(mol, auxmol)
+    env[8] = mol._env[8]
+    loc, aloc = mol.ao_loc_nr(cart=False), auxmol.ao_loc_nr(cart=False)
+    loc = np.ascontiguousarray(loc, dtype=np.int32)
+    aloc = np.ascontiguousarray(aloc, dtype=np.int32)
+    pairs = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+    dims = (loc[pairs[:, 0] + 1] - loc[pairs[:, 0]]).astype(np.int64) * (loc[pairs[:, 1] + 1] - loc[pairs[:, 1]])
+    col0 = np.ascontiguousarray(np.concatenate([[0], np.cumsum(dims)[:-1]]), dtype=np.int64)
+    ncol, naux = int(dims.sum()), int(aloc[-1])
+    out = np.zeros((naux, ncol))
+    lib().oracle_fill_int3c2e_pairs(_p(out), ctypes.c_long(ncol), ctypes.c_int(len(pairs)), _ip(pairs),
+                                    col0.ctypes.data_as(ctypes.POINTER(ctypes.c_long)), ctypes.c_int(naux), _ip(loc), _ip(aloc),
+                                    ctypes.c_int(mol.nbas), ctypes.c_int(auxmol.nbas), _ip(atm), ctypes.c_int(len(atm)),
+                                    _ip(bas), ctypes.c_int(len(bas)), _p(env))
+    return out, col0
+
+
 def int2c2e(auxmol, omega=None):
     atm, bas, env = _tables(auxmol)
     if omega is not None:

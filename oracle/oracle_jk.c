@@ -205,6 +205,30 @@ void oracle_fill_int3c2e(double *out, int nao, int naux, const int *ao_loc, cons
             }
 }
 
+/* (ij|P) for a LIST of AO shell pairs (tools/make_golden_df_size.py: sampled columns and shell slabs of the 3-center
+ * tensor at configuration size): out C-order [naux][ncol]; pair p = (pairs[2p], pairs[2p+1]) owns the columns
+ * col0[p] + a * dj + b, a < di, b < dj.  Same table conventions as oracle_fill_int3c2e. */
+void oracle_fill_int3c2e_pairs(double *out, long ncol, int npair, const int *pairs, const long *col0, int naux,
+                               const int *ao_loc, const int *aux_loc, int nbas_ao, int nbas_aux, int *atm, int natm, int *bas,
+                               int nbas, double *env)
+{
+#pragma omp parallel for schedule(dynamic, 1) collapse(2)
+    for (int p = 0; p < npair; p++)
+        for (int k = 0; k < nbas_aux; k++) {
+            int i = pairs[2 * p], j = pairs[2 * p + 1];
+            int shls[3] = {i, j, nbas_ao + k};
+            int di = ao_loc[i + 1] - ao_loc[i], dj = ao_loc[j + 1] - ao_loc[j];
+            int k0 = aux_loc[k], dk = aux_loc[k + 1] - k0;
+            double *b = malloc(sizeof(double) * di * dj * dk);
+            int3c2e_sph(b, NULL, shls, atm, natm, bas, nbas, env, NULL, NULL);
+            for (int c = 0; c < dk; c++)
+                for (int bb = 0; bb < dj; bb++)
+                    for (int a = 0; a < di; a++)
+                        out[(long)(k0 + c) * ncol + col0[p] + (long)a * dj + bb] = b[a + di * (bb + (long)dj * c)];
+            free(b);
+        }
+}
+
 /* (P|Q): out C-order [n,n] over shells [sh0, sh1) of the given tables */
 void oracle_fill_int2c2e(double *out, int n, const int *loc, int sh0, int sh1, int *atm, int natm, int *bas, int nbas,
                          double *env)

@@ -66,7 +66,8 @@ struct DFState {
 #ifndef B200JK_EMULATE
     cublasHandle_t cublas = nullptr;
     cusolverDnHandle_t cusolver = nullptr;
-    i8g::SliceStack SA, SC, SY;
+    i8g::SliceStack SA, SC, SY, SG;
+    int* d_rowexp = nullptr;   // [nrow][nao] exponents of the rows (P, a) of the unpacked tensor (made once, first tensor-core K call)
     bool sa_persistent = false; int sa_ns = 0, sa_lo = 0, sa_hi = 0;   // slices of the whole unpacked tensor kept resident (memory permitting)
     // per-stage device timers of the last b200jk_df_jk call (CUDA events on the launching stream, read after the final sync)
     std::vector<cudaEvent_t> tm_ev; std::vector<int> tm_tag; size_t tm_used = 0;
@@ -91,7 +92,8 @@ void df_free(DFState* d)
     dev_free(d->d_dmtril); dev_free(d->d_rho); dev_free(d->d_vjtril); dev_free(d->d_A); dev_free(d->d_Y); dev_free(d->d_occ);
     dev_free(d->d_dm); dev_free(d->d_vk); dev_free(d->d_vj); dev_free(d->d_Y2); dev_free(d->d_occT);
 #ifndef B200JK_EMULATE
-    d->SA.release(); d->SC.release(); d->SY.release();
+    d->SA.release(); d->SC.release(); d->SY.release(); d->SG.release();
+    dev_free(d->d_rowexp);
     if (d->cublas) cublasDestroy(d->cublas);
     if (d->cusolver) cusolverDnDestroy(d->cusolver);
 #endif
@@ -180,6 +182,16 @@ struct UnpackFn {
     }
 };
 
+struct UnpackLongFn {   // G[l][P * nao + k] = A_P[l][k] from the packed rows r0 + P: the unpacked block as nao long rows
+    const double* tril; double* out; int nao; long npair; int r0; long ld;
+    B2_HD void operator()(long idx) const
+    {
+        long l = idx / ld, e = idx - l * ld;
+        long P = e / nao, k = e - P * nao;
+        long hi = l >= k ? l : k, lo = l >= k ? k : l;
+        out[idx] = tril[(r0 + P) * npair + hi * (hi + 1) / 2 + lo];
+    }
+};
 struct IdentityFn { double* a; int n; B2_HD void operator()(long i) const { a[i * (long)n + i] = 1.0; } };
 struct GatherRowsFn {   // out[i][j] = X_colmajor[(r0+i), j]
     const double* x; double* out; int n, r0;
@@ -787,6 +799,34 @@ extern "C" int b200jk_df_local_rows(b200jk_handle h, int* row0, int* nrow)
     return 0;
 }
 
+// Columns cols[ncols] (packed AO-pair indices mu(mu+1)/2+nu) of all LOCAL rows: out[nrow][ncols] — what numpy slicing
+// dfobj._cderi[:, cols] gives on the reference's ndarray tensor (pyscf/df/df.py:116); samples a tensor too large to copy.
+struct GatherColsFn {
+    const double* cderi; const long* cols; double* out; long npair; int ncols;
+    B2_HD void operator()(long idx) const { long r = idx / ncols; int c = (int)(idx - r * ncols); out[idx] = cderi[r * npair + cols[c]]; }
+};
+extern "C" int b200jk_df_get_cderi_cols(b200jk_handle h, double* out, const int64_t* cols, int ncols)
+{
+    if (!h || !h->df || !h->df->d_cderi) { set_err(h, "call b200jk_df_build first"); return 1; }
+    try {
+        DFState* d = h->df;
+        if (!out || !cols || ncols < 1) throw std::runtime_error("bad arguments");
+        for (int c = 0; c < ncols; c++)
+            if (cols[c] < 0 || cols[c] >= d->npair) throw std::runtime_error("column index out of range");
+        if (d->nrow < 1) return 0;
+        static_assert(sizeof(long) == sizeof(int64_t), "LP64");
+        long* d_cols = (long*)dev_alloc((size_t)ncols * 8);
+        double* d_out = (double*)dev_alloc((size_t)d->nrow * ncols * 8);
+        h2d(d_cols, cols, (size_t)ncols * 8);
+        GatherColsFn g{d->d_cderi, d_cols, d_out, d->npair, ncols};
+        launch_1d((long)d->nrow * ncols, g, 0);
+        d2h(out, d_out, (size_t)d->nrow * ncols * 8);
+        dev_sync();
+        dev_free(d_cols); dev_free(d_out);
+    } catch (std::exception& e) { set_err(h, e.what()); return 2; }
+    return 0;
+}
+
 // cderi rows [r0, r0+nr) copied to the host (tests, interchange with PySCF's with_df._cderi)
 extern "C" int b200jk_df_get_cderi(b200jk_handle h, double* out, int r0, int nr)
 {
@@ -809,7 +849,6 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
         if (!d || !d->d_cderi) throw std::runtime_error("call b200jk_df_build before b200jk_df_jk");
         if (nao != h->nsph) throw std::runtime_error("nao does not match the basis of this handle");
         if (n_dm < 1) throw std::runtime_error("n_dm < 1");
-        (void)hermi;
         auto t0 = std::chrono::steady_clock::now();
         const long npair = d->npair, n2 = (long)nao * nao;
         const int naux = std::max(d->nrow, 1);   // rows held locally
@@ -915,13 +954,22 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
             }
             dev_zero(d->d_vk, (size_t)n_dm * n2 * 8, st);
 #ifndef B200JK_EMULATE
-            const bool tc = use_occ && d->k_mode == 1;
+            // tensor-core engine (k_mode 1): the occupied-orbital algorithm when the density carries its orbitals
+            // (pyscf/df/df_jk.py:339-357), else the general-density algorithm (df_jk.py:382-408) with the density itself as
+            // the right factor: Y[nu,(P,k)] = sum_mu A_P[nu,mu] D[mu,k], K[i,l] = sum_(P,k) Y[i,(P,k)] A_P[l,k] — the same two
+            // int8-slice GEMM stages, no cuBLAS
+            const bool tc = d->k_mode == 1;
+            const bool k_sym = use_occ || hermi == 1;   // the result is symmetric: compute the upper triangle, mirror at the end
             if (tc) {
                 // int32 accumulation bound: pairs(<=ns) * K * 64*64 < 2^31
                 int kmax = (int)((1L << 19) / d->k_slices);
-                kb = std::max(1, std::min(kb, kmax / nocc));
-                if ((size_t)kb * nocc * nao > d->y2_cap) { dev_free(d->d_Y2); d->y2_cap = (size_t)kb * nocc * nao; d->d_Y2 = (double*)dev_alloc(d->y2_cap * 8); }
-                if ((size_t)nocc * nao > d->occT_cap) { dev_free(d->d_occT); d->occT_cap = (size_t)nocc * nao; d->d_occT = (double*)dev_alloc(d->occT_cap * 8); }
+                kb = std::max(1, std::min(kb, kmax / ncol));
+                if ((size_t)kb * ncol * nao > d->y2_cap) { dev_free(d->d_Y2); d->y2_cap = (size_t)kb * ncol * nao; d->d_Y2 = (double*)dev_alloc(d->y2_cap * 8); }
+                if ((size_t)ncol * nao > d->occT_cap) { dev_free(d->d_occT); d->occT_cap = (size_t)ncol * nao; d->d_occT = (double*)dev_alloc(d->occT_cap * 8); }
+                if (!d->d_rowexp) {
+                    d->d_rowexp = (int*)dev_alloc((size_t)std::max(d->nrow, 1) * nao * 4);
+                    i8g::packed_rowexp(d->d_cderi, npair, nao, d->nrow, d->d_rowexp, st);
+                }
             }
 #endif
 #ifndef B200JK_EMULATE
@@ -936,12 +984,8 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
                     d->SA.alloc((int)rows_tot, nao, d->k_slices);
                     CK(cudaMemsetAsync(d->SA.q, 0, need, st));
                     CK(cudaMemsetAsync(d->SA.E, 0, rp * 4, st));
-                    for (int r0 = r_lo; r0 < r_hi; r0 += kb) {
-                        int nr = std::min(kb, r_hi - r0);
-                        UnpackFn up{d->d_cderi, d->d_A, nao, npair, r0};
-                        launch_1d((long)nr * n2, up, st);
-                        i8g::split_rows_into(d->SA, (r0 - r_lo) * nao, d->d_A, nao, nr * nao, st);
-                    }
+                    i8g::split_packed_into(d->SA, 0, d->d_cderi + (size_t)r_lo * npair, npair, nao, r_hi - r_lo,
+                                           d->d_rowexp + (size_t)r_lo * nao, st);
                     d->sa_persistent = true; d->sa_ns = d->k_slices; d->sa_lo = r_lo; d->sa_hi = r_hi;
                 }
             }
@@ -949,10 +993,24 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
             for (int r0 = r_lo; r0 < r_hi; r0 += kb) {
                 int nr = std::min(kb, r_hi - r0);
 #ifndef B200JK_EMULATE
-                if (!(tc && d->sa_persistent)) {
+                if (tc) {
+                    if (!d->sa_persistent) {    // slices of this block straight from the packed rows
+                        mark(B200JK_DF_STAGE_K_SLICE);
+                        i8g::split_packed(d->SA, d->d_cderi + (size_t)r0 * npair, npair, nao, nr, d->d_rowexp + (size_t)r0 * nao, d->k_slices, st);
+                        mark(-1);
+                        launches++;
+                    }
+                    if (!use_occ) {             // general density: the block once more as nao long rows G[l][(P,k)] = A_P[l][k]
+                        mark(B200JK_DF_STAGE_K_SLICE);
+                        UnpackLongFn ul{d->d_cderi, d->d_A, nao, npair, r0, (long)nr * nao};
+                        launch_1d((long)nr * n2, ul, st);
+                        i8g::split_rows(d->SG, d->d_A, (long)nr * nao, nao, nr * nao, d->k_slices, st);
+                        mark(-1);
+                        launches += 2;
+                    }
+                } else {
                     UnpackFn up{d->d_cderi, d->d_A, nao, npair, r0};
                     launch_1d((long)nr * n2, up, st); launches++;
-                    if (tc) { i8g::split_rows(d->SA, d->d_A, nao, nr * nao, nao, d->k_slices, st); launches++; }
                 }
 #else
                 UnpackFn up{d->d_cderi, d->d_A, nao, npair, r0};
@@ -964,9 +1022,10 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
                     if (tc) {
                         // tcgen05 path: Y2[nu][(P,i)] = sum_mu A_P[nu,mu] Ct[i,mu] ; K += Y2 Y2^T (upper triangle)
                         if (r0 == r_lo || n_dm > 1) {
-                            TransposeFn tr{d->d_occ + (size_t)s * nao * nocc, d->d_occT, nao, nocc};
-                            launch_1d((long)nao * nocc, tr, st);
-                            i8g::split_rows(d->SC, d->d_occT, nao, nocc, nao, d->k_slices, st); launches += 2;
+                            // right factor of stage 1 as rows [ncol][nao]: C~^T, or D^T for the general-density algorithm
+                            TransposeFn tr{use_occ ? d->d_occ + (size_t)s * nao * nocc : d->d_dm + (size_t)s * n2, d->d_occT, nao, ncol};
+                            launch_1d((long)nao * ncol, tr, st);
+                            i8g::split_rows(d->SC, d->d_occT, nao, ncol, nao, d->k_slices, st); launches += 2;
                         }
                         static const bool prof = getenv("B200JK_DF_PROFILE") != nullptr;
                         static double tacc[5];
@@ -981,13 +1040,14 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
                         tick(-1);
                         tick(0);
                         mark(B200JK_DF_STAGE_K_GEMM1);
-                        i8g::gemm_ar(d->SA, d->sa_persistent ? (r0 - r_lo) * nao : 0, nr * nao, d->SC, d->d_Y2, (long)nr * nocc, nao, st);
+                        i8g::gemm_ar(d->SA, d->sa_persistent ? (r0 - r_lo) * nao : 0, nr * nao, d->SC, d->d_Y2, (long)nr * ncol, nao, st);
                         tick(1);
                         mark(B200JK_DF_STAGE_K_SLICE);
-                        i8g::split_rows(d->SY, d->d_Y2, (long)nr * nocc, nao, nr * nocc, d->k_slices, st);
+                        i8g::split_rows(d->SY, d->d_Y2, (long)nr * ncol, nao, nr * ncol, d->k_slices, st);
                         tick(2);
                         mark(B200JK_DF_STAGE_K_GEMM2);
-                        i8g::gemm(d->SY, d->SY, d->d_vk + (size_t)s * n2, nao, 0, true, st);
+                        // K += Y Y^T (orbitals) or Y G^T (general density; only its upper triangle when D, hence K, is symmetric)
+                        i8g::gemm(d->SY, use_occ ? d->SY : d->SG, d->d_vk + (size_t)s * n2, nao, 0, k_sym, st);
                         mark(-1);
                         tick(3);
                         if (prof && r0 + kb >= r_hi) {
@@ -1060,7 +1120,7 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
                 }
             }
 #ifndef B200JK_EMULATE
-            if (use_occ && d->k_mode == 1) { MirrorUpperFn mf{d->d_vk, nao}; for (int s = 0; s < n_dm; s++) { mf.a = d->d_vk + (size_t)s * n2; launch_1d(n2, mf, st); launches++; } }
+            if (tc && k_sym) { MirrorUpperFn mf{d->d_vk, nao}; for (int s = 0; s < n_dm; s++) { mf.a = d->d_vk + (size_t)s * n2; launch_1d(n2, mf, st); launches++; } }
 #endif
             if (!on_device) d2h(vk, d->d_vk, (size_t)n_dm * n2 * 8, st);
             else {

@@ -72,6 +72,45 @@ void split_rows(SliceStack& S, const double* X, long ldx, int rows, int k, int n
     CK(cudaGetLastError());
 }
 
+// ---- the DF tensor from its packed rows (see i8gemm.cuh (3)) ----
+// rowexp[nr][nao]: exponent of every row (P, a) of the unpacked tensor; cderi points at the first of the nr packed rows
+void packed_rowexp(const double* cderi, long npair, int nao, int nr, int* rowexp, cudaStream_t st)
+{
+    CK(cudaMemsetAsync(rowexp, 0x80, (size_t)nr * nao * 4, st));     // EXP_NONE
+    static bool configured = false;
+    if (!configured) { CK(cudaFuncSetAttribute(packed_rowexp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); configured = true; }
+    if ((size_t)nao * 4 > 160 * 1024) throw std::runtime_error("packed_rowexp: nao too large for the shared-memory exponent table");
+    for (int p0 = 0; p0 < nr; p0 += 32768) {
+        int n = std::min(32768, nr - p0);
+        packed_rowexp_kernel<<<dim3((nao + 63) / 64, n), 256, (size_t)nao * 4, st>>>(cderi + (size_t)p0 * npair, npair, nao, rowexp + (size_t)p0 * nao);
+    }
+    CK(cudaGetLastError());
+}
+// slices of the unpacked rows (P, a), P in [0, nr), into the rows out_row0 + P nao + a of an allocated stack
+void split_packed_into(SliceStack& S, int out_row0, const double* cderi, long npair, int nao, int nr, const int* rowexp, cudaStream_t st)
+{
+    if (S.K != nao) throw std::runtime_error("split_packed: stack width does not match nao");
+    const unsigned nt = (unsigned)(S.Kp / PT);
+    for (int p0 = 0; p0 < nr; p0 += 32768) {
+        int n = std::min(32768, nr - p0);
+        split_packed_kernel<<<dim3(nt, nt, n), 256, 0, st>>>(cderi + (size_t)p0 * npair, npair, nao, rowexp + (size_t)p0 * nao, S.ns, S.Rp, S.Kp,
+                                                             out_row0 + p0 * nao, S.q, S.E);
+    }
+    CK(cudaGetLastError());
+}
+// a stack holding exactly these nr packed rows (allocated here, pad rows zeroed)
+void split_packed(SliceStack& S, const double* cderi, long npair, int nao, int nr, const int* rowexp, int ns, cudaStream_t st)
+{
+    const int rows = nr * nao;
+    S.alloc(rows, nao, ns);
+    if (S.Rp > rows) {
+        for (int s = 0; s < ns; s++)
+            CK(cudaMemsetAsync(S.q + ((size_t)s * S.Rp + rows) * S.Kp, 0, (size_t)(S.Rp - rows) * S.Kp, st));
+        CK(cudaMemsetAsync(S.E + rows, 0, (size_t)(S.Rp - rows) * 4, st));
+    }
+    split_packed_into(S, 0, cderi, npair, nao, nr, rowexp, st);
+}
+
 // stage-1 GEMM of DF-K with all slice-pair groups resident in TMEM (i8gemm_ar_kernel): rows [a_row0, a_row0+M) of A
 void gemm_ar(const SliceStack& A, int a_row0, int M, const SliceStack& B, double* C, long ldc, int inner, cudaStream_t st)
 {

@@ -542,6 +542,102 @@ __global__ void __launch_bounds__(256) split_long_kernel(const double* __restric
     }
 }
 
+
+// (3) the DF tensor, straight from its PACKED rows (reference layout cderi[P][a(a+1)/2 + b], a >= b, pyscf/df/incore.py:134-136)
+//     to the int8 slices of the UNPACKED matrices A_P[a][b] = A_P[b][a] that stage 1 of DF-K multiplies: no fp64 unpacked
+//     copy is ever written.  Row (P, a) of the stack is scaled by its own exponent (max over the whole unpacked row).
+constexpr int EXP_NONE = (int)0x80808080;    // "no non-zero element seen yet" (byte pattern of a memset with 0x80)
+__device__ __forceinline__ int frexp_exp(double v)   // e with |v| = f 2^e, f in [0.5, 1); v != 0
+{
+    return (int)((__double_as_longlong(v) >> 52) & 0x7ff) - 1022;
+}
+// rowexp[P][a] = exponent of max_b |A_P[a][b]|, accumulated with integer atomicMax; the caller fills rowexp with EXP_NONE.
+// grid (ceil(nao / 64), nr): a CTA reads the packed rows a0 .. a0+63 of auxiliary row P once, coalesced; an element (a, b)
+// counts for row a (warp reduction) and for row b (shared-memory atomicMax, flushed once per CTA).
+__global__ void __launch_bounds__(256) packed_rowexp_kernel(const double* __restrict__ cderi, long npair, int nao, int* __restrict__ rowexp)
+{
+    extern __shared__ int emax_s[];          // [nao]
+    const int P = blockIdx.y;
+    const double* row = cderi + (long)P * npair;
+    const int a0 = blockIdx.x * 64, a1 = (a0 + 64 < nao) ? a0 + 64 : nao;
+    for (int b = threadIdx.x; b < a1; b += 256) emax_s[b] = EXP_NONE;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int a = a0 + warp; a < a1; a += 8) {
+        const double* x = row + (long)a * (a + 1) / 2;
+        int em = EXP_NONE;
+        for (int b = lane; b <= a; b += 32) {
+            const double v = fabs(x[b]);
+            if (v > 0.0) {
+                const int e = frexp_exp(v);
+                em = e > em ? e : em;
+                if (e > emax_s[b]) atomicMax(&emax_s[b], e);
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, em, o); em = t > em ? t : em; }
+        if (lane == 0 && em != EXP_NONE) atomicMax(&rowexp[(long)P * nao + a], em);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < a1; b += 256)
+        if (emax_s[b] != EXP_NONE) atomicMax(&rowexp[(long)P * nao + b], emax_s[b]);
+}
+
+constexpr int PT = 64;   // tile edge of split_packed_kernel
+// grid (Kp/PT, Kp/PT, nr), CTAs with tile column > tile row leave at once.  CTA (ta, tb, P): loads the 64 x 64 tile
+// A_P[ta*64 .., tb*64 ..] from the packed row (coalesced: 64 consecutive doubles per a), writes its slices to the rows
+// (P, a) at columns b and — for off-diagonal tiles — the slices of the transposed tile to the rows (P, b) at columns a,
+// four int8 per 32-bit store.  Columns nao..Kp-1 are written as zeros; pad ROWS of the stack are the caller's (memset).
+__global__ void __launch_bounds__(256) split_packed_kernel(const double* __restrict__ cderi, long npair, int nao,
+                                                           const int* __restrict__ rowexp, int ns, int Rp, int Kp, int out_row0,
+                                                           int8_t* __restrict__ out, int* __restrict__ E)
+{
+    const int ta = blockIdx.x, tb = blockIdx.y, P = blockIdx.z;
+    if (tb > ta) return;
+    __shared__ double S[PT][PT + 1];
+    const double* row = cderi + (long)P * npair;
+    const int* ex = rowexp + (long)P * nao;
+    const int t = threadIdx.x;
+#pragma unroll 4
+    for (int i = 0; i < PT * PT / 256; i++) {
+        const int idx = t + 256 * i, al = idx >> 6, bl = idx & 63;
+        const int a = ta * PT + al, b = tb * PT + bl;
+        double v = 0.0;
+        if (a < nao && b < nao) { const int hi = a > b ? a : b, lo = a > b ? b : a; v = row[(long)hi * (hi + 1) / 2 + lo]; }
+        S[al][bl] = v;
+    }
+    __syncthreads();
+    const int c4 = (t & 15) * 4;     // four consecutive output columns per thread
+    const long orow0 = (long)out_row0 + (long)P * nao;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1 && ta == tb) break;
+        const int trow = pass ? tb : ta, tcol = pass ? ta : tb;    // output rows / columns of this pass
+#pragma unroll 1
+        for (int i = 0; i < 4; i++) {
+            const int rl = (t >> 4) + 16 * i;
+            const int r = trow * PT + rl;
+            if (r >= nao) continue;
+            int e = ex[r];
+            if (e == EXP_NONE) e = 0;
+            if (tcol == 0 && c4 == 0) E[orow0 + r] = e;
+            const double sc = pow2i(6 - e);
+            double rr[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) rr[j] = (pass ? S[c4 + j][rl] : S[rl][c4 + j]) * sc;
+            int8_t* dst = out + (orow0 + r) * Kp + tcol * PT + c4;
+            for (int s_ = 0; s_ < ns; s_++) {
+                unsigned pack = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const double qv = rint(rr[j]);
+                    pack |= (unsigned)(unsigned char)(int8_t)(int)qv << (8 * j);
+                    rr[j] = (rr[j] - qv) * 128.0;
+                }
+                *reinterpret_cast<unsigned*>(dst + (long)s_ * Rp * Kp) = pack;
+            }
+        }
+    }
+}
+
 }  // namespace i8g
 }  // namespace b200jk
-

@@ -14,6 +14,11 @@ struct SliceStack {      // [ns][Rp][Kp] int8 slices + per-row exponents, device
 };
 void split_rows(SliceStack& S, const double* X, long ldx, int rows, int k, int ns, cudaStream_t st);
 void split_rows_into(SliceStack& S, int row0, const double* X, long ldx, int rows, cudaStream_t st);
+// the DF tensor straight from its packed rows cderi[P][a(a+1)/2+b] (no fp64 unpacked copy): per-row exponents of the unpacked
+// rows (P, a), then their int8 slices
+void packed_rowexp(const double* cderi, long npair, int nao, int nr, int* rowexp, cudaStream_t st);
+void split_packed_into(SliceStack& S, int out_row0, const double* cderi, long npair, int nao, int nr, const int* rowexp, cudaStream_t st);
+void split_packed(SliceStack& S, const double* cderi, long npair, int nao, int nr, const int* rowexp, int ns, cudaStream_t st);
 void gemm_ar(const SliceStack& A, int a_row0, int M, const SliceStack& B, double* C, long ldc, int inner, cudaStream_t st);
 // C[m*ldc + n] (or the transposed scatter when inner>0, see GemmParams) += A B^T
 void gemm(const SliceStack& A, const SliceStack& B, double* C, long ldc, int inner, bool symmetric, cudaStream_t st,

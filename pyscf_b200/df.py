@@ -145,6 +145,19 @@ class DF:
             h.check(h.lib.b200jk_df_get_cderi(h._h, _lib.dptr(buf), r0, nr), 'b200jk_df_get_cderi')
             yield buf
 
+    def cderi_columns(self, cols):
+        """cderi[:, cols] for packed AO-pair indices `cols` (mu(mu+1)/2 + nu, mu >= nu), rows held by this rank — numpy slicing
+        of the reference's ndarray tensor (pyscf/df/df.py:116) without copying the tensor to the host."""
+        self.get_naoaux()
+        h = self._handle
+        row0, nrow = ctypes.c_int(0), ctypes.c_int(0)
+        h.check(h.lib.b200jk_df_local_rows(h._h, ctypes.byref(row0), ctypes.byref(nrow)), 'b200jk_df_local_rows')
+        cols = np.ascontiguousarray(cols, dtype=np.int64)
+        out = np.empty((nrow.value, len(cols)))
+        h.check(h.lib.b200jk_df_get_cderi_cols(h._h, _lib.dptr(out), cols.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), len(cols)),
+                'b200jk_df_get_cderi_cols')
+        return out
+
     @property
     def _cderi(self):
         return np.vstack(list(self.loop()))

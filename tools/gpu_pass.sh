@@ -17,6 +17,9 @@ for step in "$@"; do
             head -c 3000 gpurun_out/${TAG}_bench_nodf.json ;;
     ref)    timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${TAG}_ref.json 2> gpurun_out/${TAG}_ref.err
             head -c 3000 gpurun_out/${TAG}_ref.json ;;
+    pytest:*) timeout 1500 python -m pytest tests -m gpu -x -q -s -k "${step#pytest:}" 2>&1 | tail -30 | tee gpurun_out/${TAG}_pytest.txt ;;
+    bench:*) W=${step#bench:}; timeout 900 python bench.py --workload $W --steps 5 --warmup 3 > gpurun_out/${TAG}_bench_$W.json 2> gpurun_out/${TAG}_bench_$W.err
+            tail -c 800 gpurun_out/${TAG}_bench_$W.err; python tools/bench_brief.py gpurun_out/${TAG}_bench_$W.json ;;
     smoke)  timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -8 | tee gpurun_out/${TAG}_smoke.txt ;;
     *)      echo "unknown step $step" ;;
   esac
