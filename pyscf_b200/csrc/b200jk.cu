@@ -333,16 +333,60 @@ static int direct_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, 
                 if (B.kept.empty() || K.kept.empty()) continue;
                 double nq = (double)B.kept.size() * K.kept.size() * (cb == ck ? 0.5 : 1.0);
                 double ncomp = (double)ncart(B.la) * ncart(B.lb) * ncart(K.la) * ncart(K.lb);
-                jobs.push_back({cb, ck, nq * (ncomp + 50.0) * ((B.la + B.lb + K.la + K.lb) / 2 + 1)});
+                double pb = 0, pk = 0;     // primitive pairs on either side -> primitive quartets of the class
+                for (const ShellPair& sp : B.kept) pb += sp.nprim;
+                for (const ShellPair& sp : K.kept) pk += sp.nprim;
+                double pq = pb * pk * (cb == ck ? 0.5 : 1.0);
+                int nr = (B.la + B.lb + K.la + K.lb) / 2 + 1;
+                // milliseconds on one B200: least-squares fit to the measured class times of benzene/cc-pVTZ
+                // (profiles/r01_class_times_direct.json, mean abs error 20 %): launch/tail + roots + root sum + digestion
+                jobs.push_back({cb, ck, 0.0976 + 3.14e-9 * pq * nr + 7.6e-10 * pq * nr * ncomp + 2.38e-9 * nq * ncomp + 1.3e-7 * nq});
             }
         std::sort(jobs.begin(), jobs.end(), [](const Job& a, const Job& b) { return a.cost > b.cost; });
+        // Multi-GPU partition (reference analogue: omp schedule(dynamic) over AO-block triples, pyscf/lib/vhf/nr_direct.c:429-466).
+        // The big classes are split over the ranks by bra pair (round-robin on the cost-sorted lists).  The small ones would shrink
+        // to a few CTAs per rank and cost every rank their launch-and-tail latency, so they are given WHOLE to one rank each,
+        // longest-processing-time first on the cost model above; every rank takes the same decisions from the same tables.
+        std::vector<int> owner(jobs.size(), -1);   // -1: split over all ranks
+        if (h->shard_world > 1) {
+            const int W = h->shard_world;
+            double total = 0;
+            for (const Job& jb : jobs) total += jb.cost;
+            double cum = 0;
+            size_t first_whole = jobs.size();
+            for (size_t i = jobs.size(); i-- > 0;) {       // from the cheapest class upwards
+                if (jobs[i].cost > total / (3.0 * W) || cum + jobs[i].cost > 0.45 * total) break;
+                cum += jobs[i].cost;
+                first_whole = i;
+            }
+            std::vector<double> load(W, 0.0);
+            for (size_t i = first_whole; i < jobs.size(); i++) {
+                int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+                owner[i] = r;
+                load[r] += jobs[i].cost;
+            }
+        }
 #ifndef B200JK_EMULATE
         CK(cudaEventRecord(h->ev_in, st));
         for (auto& s : h->side) CK(cudaStreamWaitEvent(s, h->ev_in, 0));
 #endif
         int jn = 0;
-        for (const Job& jb : jobs) {
+        for (size_t ji = 0; ji < jobs.size(); ji++) {
+            const Job& jb = jobs[ji];
             int cb = jb.cb, ck = jb.ck;
+            if (owner[ji] >= 0) {                       // a class given whole to one rank
+                if (owner[ji] != h->shard_rank) {
+#ifndef B200JK_EMULATE
+                    if (h->profile) {     // keep the per-class timers readable: an empty interval
+                        if (h->cls_ev.empty()) { h->cls_ev.resize(2 * NPC * NPC); for (auto& e : h->cls_ev) CK(cudaEventCreate(&e)); }
+                        CK(cudaEventRecord(h->cls_ev[2 * (cb * NPC + ck)], st));
+                        CK(cudaEventRecord(h->cls_ev[2 * (cb * NPC + ck) + 1], st));
+                    }
+#endif
+                    continue;
+                }
+                P.shard_rank = 0; P.shard_world = 1;
+            } else { P.shard_rank = h->shard_rank; P.shard_world = h->shard_world; }
             PairClass &B = h->pc[cb], &K = h->pc[ck];
             // (measured: the thread-per-quartet kernels are also faster on the split lists — balance beats the extra digestions)
             P.bra_pairs = B.d_kept; P.nbra = (int)B.kept.size();

@@ -219,50 +219,76 @@ struct UnpackTrilFn {   // vj[s][i][j] from vjtril[s][t]
 };
 
 #ifndef B200JK_EMULATE
-// rho[s][P] += sum_{t in segment} cderi[P][t] dmtril[s][t]  — grid (segments, rows, dms); coalesced, atomics on rho
+// rho[s][P] += sum_{t in segment} cderi[P][t] dmtril[s][t]  — grid (segments, groups of DFJ_R rows, dms).  A thread multiplies ONE
+// density element with DFJ_R rows: the tensor streams from HBM once while the density vector comes out of L2 once per DFJ_R rows
+// (one row at a time, the L2 -> SM traffic is twice the HBM stream and caps the kernel at ~55 % of the HBM peak).
+constexpr int DFJ_R = 8;
 __global__ void __launch_bounds__(256) dfj_rho_kernel(const double* __restrict__ cderi, const double* __restrict__ dmtril,
-                                                      double* __restrict__ rho, long npair, long r0, int naux, long seglen)
+                                                      double* __restrict__ rho, long npair, long r0, long r_end, int naux, long seglen)
 {
-    const long r = r0 + blockIdx.y;
+    const long rb = r0 + (long)blockIdx.y * DFJ_R;
+    const int nr = (int)((r_end - rb < DFJ_R) ? r_end - rb : DFJ_R);
     const int s = blockIdx.z;
     const long t0 = blockIdx.x * seglen;
     const long t1 = (t0 + seglen < npair) ? t0 + seglen : npair;
-    const double* row = cderi + r * npair;
+    const double* row = cderi + rb * npair;
     const double* d = dmtril + (long)s * npair;
-    double acc0 = 0.0, acc1 = 0.0;
-    long t = t0 + threadIdx.x;
-    for (; t + 256 < t1; t += 512) { acc0 += row[t] * d[t]; acc1 += row[t + 256] * d[t + 256]; }
-    for (; t < t1; t += 256) acc0 += row[t] * d[t];
-    double acc = acc0 + acc1;
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    __shared__ double part[8];
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    double acc[DFJ_R];
+#pragma unroll
+    for (int r = 0; r < DFJ_R; r++) acc[r] = 0.0;
+    if (nr == DFJ_R) {
+#pragma unroll 2
+        for (long t = t0 + threadIdx.x; t < t1; t += 256) {
+            const double dv = d[t];
+#pragma unroll
+            for (int r = 0; r < DFJ_R; r++) acc[r] += __ldcs(row + r * npair + t) * dv;     // streamed once: evict first
+        }
+    } else {
+        for (long t = t0 + threadIdx.x; t < t1; t += 256) {
+            const double dv = d[t];
+#pragma unroll
+            for (int r = 0; r < DFJ_R; r++)
+                if (r < nr) acc[r] += __ldcs(row + r * npair + t) * dv;
+        }
+    }
+    __shared__ double part[8][DFJ_R];
+#pragma unroll
+    for (int r = 0; r < DFJ_R; r++) {
+        double a = acc[r];
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5][r] = a;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < nr) {
         double tot = 0.0;
-        for (int w = 0; w < 8; w++) tot += part[w];
-        atomicAdd(&rho[(long)s * naux + r], tot);
+        for (int w = 0; w < 8; w++) tot += part[w][threadIdx.x];
+        atomicAdd(&rho[(long)s * naux + rb + threadIdx.x], tot);
     }
 }
-// vjtril[s][t] += sum_{P in block} rho[s][P] cderi[P][t]  — thread per column, rows just read stay in L2
+// vjtril[s][t] += sum_{P in this CTA's row range} rho[s][P] cderi[P][t]  — thread per column, grid (column blocks, row ranges): the
+// row ranges make the launch many waves deep (one row range = 1.2 waves on C60: 30 % of the time in a nearly empty second wave)
 __global__ void __launch_bounds__(256) dfj_acc_kernel(const double* __restrict__ cderi, const double* __restrict__ rho,
                                                       double* __restrict__ vjtril, long npair, long r0, int nr, int naux, int n_dm)
 {
     long t = blockIdx.x * 256L + threadIdx.x;
     if (t >= npair) return;
+    const int per = (nr + gridDim.y - 1) / gridDim.y;
+    const int ra = blockIdx.y * per, rb = (ra + per < nr) ? ra + per : nr;
     for (int s = 0; s < n_dm; s++) {
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         const double* rh = rho + (long)s * naux + r0;
         const double* col = cderi + r0 * npair + t;
-        int r = 0;
-        for (; r + 4 <= nr; r += 4) {
-            a0 += rh[r] * col[(long)r * npair];
-            a1 += rh[r + 1] * col[(long)(r + 1) * npair];
-            a2 += rh[r + 2] * col[(long)(r + 2) * npair];
-            a3 += rh[r + 3] * col[(long)(r + 3) * npair];
+        int r = ra;
+        for (; r + 4 <= rb; r += 4) {
+            a0 += rh[r] * __ldcs(col + (long)r * npair);
+            a1 += rh[r + 1] * __ldcs(col + (long)(r + 1) * npair);
+            a2 += rh[r + 2] * __ldcs(col + (long)(r + 2) * npair);
+            a3 += rh[r + 3] * __ldcs(col + (long)(r + 3) * npair);
         }
-        for (; r < nr; r++) a0 += rh[r] * col[(long)r * npair];
-        vjtril[(long)s * npair + t] += (a0 + a1) + (a2 + a3);
+        for (; r < rb; r++) a0 += rh[r] * __ldcs(col + (long)r * npair);
+        const double v = (a0 + a1) + (a2 + a3);
+        if (gridDim.y == 1) vjtril[(long)s * npair + t] += v;
+        else atomicAdd(&vjtril[(long)s * npair + t], v);
     }
 }
 #endif
@@ -907,13 +933,18 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
             // two streaming passes over the tensor (rho, then J): 2 launches, both HBM-bound
             (void)rb;
             mark(B200JK_DF_STAGE_J_RHO);
-            for (int r0 = r_lo; r0 < r_hi; r0 += 32768) {
-                int nr = std::min(32768, r_hi - r0);
-                dfj_rho_kernel<<<dim3(nseg, nr, n_dm), 256, 0, st>>>(d->d_cderi, d->d_dmtril, d->d_rho, npair, r0, naux, seglen);
+            for (int r0 = r_lo; r0 < r_hi; r0 += 32768 * DFJ_R) {
+                int nr = std::min(32768 * DFJ_R, r_hi - r0);
+                dfj_rho_kernel<<<dim3(nseg, (nr + DFJ_R - 1) / DFJ_R, n_dm), 256, 0, st>>>(d->d_cderi, d->d_dmtril, d->d_rho, npair, r0, r0 + nr, naux, seglen);
                 launches++;
             }
             mark(B200JK_DF_STAGE_J_ACC);
-            dfj_acc_kernel<<<(unsigned)((npair + 255) / 256), 256, 0, st>>>(d->d_cderi, d->d_rho, d->d_vjtril, npair, r_lo, r_hi - r_lo, naux, n_dm);
+            {
+                const unsigned ncb = (unsigned)((npair + 255) / 256);
+                // >= ~6 waves of 148 x 8 CTAs, each row range >= 64 rows
+                unsigned gy = (unsigned)std::max<long>(1, std::min<long>((r_hi - r_lo) / 64, (6L * 148 * 8 + ncb - 1) / ncb));
+                dfj_acc_kernel<<<dim3(ncb, gy), 256, 0, st>>>(d->d_cderi, d->d_rho, d->d_vjtril, npair, r_lo, r_hi - r_lo, naux, n_dm);
+            }
             launches++;
             mark(-1);
             CK(cudaGetLastError());

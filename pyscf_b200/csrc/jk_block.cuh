@@ -51,10 +51,18 @@ constexpr int pow2ceil(int x) { int p = 1; while (p < x) p *= 2; return p; }
 //    once per part it holds (ncu: 20 of 32 threads active per instruction in (fd|dp)).
 //  * PPW (B2_PPW, classes with NP > 1 and NKL <= 32): a group is NP warps, warp w holds part w of QPG = 32 / NKL quartets,
 //    so no warp ever mixes parts.  Logical lane id inside a quartet stays g = part * NKL + (c,d).
+// classes that measured faster with the part-per-warp layout on B200 (benzene/cc-pVTZ, profiles/r02_ab_direct_variants.txt:
+// dd|pp -18 %, ff|ds -13 %, fd|ds -6 %, dd|dp, dd|ds, fd|pp -4..-6 %); (fd|dp), (ff|dp), (dd|ps) lose 10-35 % and stay as they were.
+// B2_PPW = 1 forces the layout for every class with NP > 1 (A/B builds), -1 switches it off everywhere.
+constexpr bool class_prefers_ppw(int li, int lj, int lk, int ll)
+{
+    return (li == 2 && lj == 2 && lk == 1 && ll == 1) || (li == 3 && lj == 3 && lk == 2 && ll == 0) || (li == 3 && lj == 2 && lk == 2 && ll == 0) ||
+           (li == 2 && lj == 2 && lk == 2 && ll == 1) || (li == 2 && lj == 2 && lk == 2 && ll == 0) || (li == 3 && lj == 2 && lk == 1 && ll == 1);
+}
 template <class C>
 struct GroupCfg {
     static constexpr int G = C::G;
-    static constexpr bool PPW = (B2_PPW != 0) && C::NP > 1 && C::NKL <= 32 && C::NP <= 8;
+    static constexpr bool PPW = (B2_PPW > 0 || (B2_PPW == 0 && class_prefers_ppw(C::LI, C::LJ, C::LK, C::LL))) && C::NP > 1 && C::NKL <= 32 && C::NP <= 8;
     static constexpr int GP = G <= 32 ? G : ((G + 31) / 32) * 32;              // lanes reserved per quartet (default layout)
     static constexpr int GW = PPW ? C::NP : (GP + 31) / 32;                  // warps per group
     static constexpr int TG = GW * 32;                                       // threads per group

@@ -442,7 +442,13 @@ B2_HD void phase_accumulate(const SlotSmem<C>& s, ThreadCtx<C>& t, double ABx, d
 }
 
 #ifdef __CUDA_ARCH__
+#ifdef B2_EXPERIMENT_NORED
+// tuning experiment only (tools/build_variant.sh nored "-DB2_EXPERIMENT_NORED"): the arithmetic stays alive, the reduction never
+// executes — an upper bound on what the write-back costs.  Results are WRONG by construction.
+__device__ __forceinline__ void red_add(double* addr, double val) { if (val == 1.2345678e301) atomicAdd(addr, val); }
+#else
 __device__ __forceinline__ void red_add(double* addr, double val) { atomicAdd(addr, val); }
+#endif
 #else
 inline void red_add(double* addr, double val) { *addr += val; }
 #endif

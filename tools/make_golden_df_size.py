@@ -46,17 +46,22 @@ def slab_coeff(nao, nocc, sao, seed=7):
 
 
 def pick_pairs(mol, rng, per_type=2):
-    """Two shell pairs (ish >= jsh) of every (l_i, l_j) type, spread over the molecule."""
-    ls = mol._bas[:, 1]
+    """Two shell pairs (ish >= jsh) of every (l_i, l_j) type, spread over the molecule; the two shells sit on the same atom
+    or on atoms closer than 2.2 Angstrom (a pair of distant shells has a vanishing tensor column, which checks nothing)."""
+    ls, at = mol._bas[:, 1], mol._bas[:, 0]
+    coords = np.array([mol._env[mol._atm[a, 1]:mol._atm[a, 1] + 3] for a in range(mol.natm)])
     out = []
     for la in sorted(set(ls)):
         for lb in sorted(set(ls)):
             if lb > la:
                 continue
-            ia, ib = np.where(ls == la)[0], np.where(ls == lb)[0]
+            ia, ib_all = np.where(ls == la)[0], np.where(ls == lb)[0]
             got = set()
             for _ in range(200):
-                i, j = int(rng.choice(ia)), int(rng.choice(ib))
+                i = int(rng.choice(ia))
+                near = ib_all[np.linalg.norm(coords[at[ib_all]] - coords[at[i]], axis=1) < 2.2 / 0.52917721092]
+                ib = near if len(near) else ib_all
+                j = int(rng.choice(ib))
                 if i < j:
                     i, j = j, i
                 if (i, j) not in got:
