@@ -137,6 +137,27 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// the same load without the wait: several loads in flight, then one tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld_32x32b_x32_nowait(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// exact int32 -> fp64 on the FP64 add pipe (one LOP + one DADD instead of a conversion instruction):
+// the double with high word 0x43300000 and low word (x ^ 2^31) is 2^52 + 2^31 + x
+__device__ __forceinline__ double i2d_exact(uint32_t x)
+{
+    return __hiloint2double(0x43300000, (int)(x ^ 0x80000000u)) - 4503601774854144.0;
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
 __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr)
@@ -328,8 +349,8 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
     uint64_t* bfull = aempty + AR_MAXA;          // [AR_NSB]
     uint64_t* bempty = bfull + AR_NSB;
     uint64_t* tfull = bempty + AR_NSB;           // [1] accumulators complete (MMA -> epilogue)
-    uint64_t* tempty = tfull + 1;                // [1] accumulators drained  (epilogue -> MMA), 4 arrivals
-    uint32_t* tmem_slot = (uint32_t*)(tempty + 1);
+    uint64_t* tempty = tfull + 1;                // [MAXS] accumulator of slice-pair group g drained (epilogue -> MMA), 4 arrivals each
+    uint32_t* tmem_slot = (uint32_t*)(tempty + MAXS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = P.Kp / BK;
@@ -342,7 +363,7 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
         for (int i = 0; i < nsa; i++) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
         for (int i = 0; i < AR_NSB; i++) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
         mbar_init(tfull, 1);
-        mbar_init(tempty, 4);
+        for (int g = 0; g < MAXS; g++) mbar_init(&tempty[g], 4);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -351,6 +372,9 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // The A slices of a K block are taken in DESCENDING order k = ns-1 .. 0: slice k multiplies B slices 0 .. ns-1-k into the
+    // groups k .. ns-1, so group g is first touched by A_g, and the next tile's MMAs can start as soon as the epilogue has
+    // drained group ns-1 (it drains in the same order) instead of waiting for the whole accumulator.
     if (warp == 0) {
         if (lane == 0) {
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
@@ -362,7 +386,7 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
                     for (int l = 0; l < ns; l++)
                         tma_load_2d(sB + sb * bstage + l * AR_B1_BYTES, &tmapB, &bfull[sb], kb * BK, l * P.Np + nt * AR_BN);
                     if (++sb == AR_NSB) { sb = 0; pb ^= 1; }
-                    for (int k = 0; k < ns; k++) {
+                    for (int k = ns - 1; k >= 0; k--) {
                         mbar_wait(&aempty[sa], pa ^ 1);
                         mbar_expect_tx(&afull[sa], AR_A_BYTES);
                         tma_load_2d(sA + sa * AR_A_BYTES, &tmapA, &afull[sa], kb * BK, k * P.Mp + P.a_row0 + mt * BM);
@@ -377,33 +401,45 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
             int it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
                 if (P.dbg && blockIdx.x == 0 && it < 6) P.dbg[it * 8 + 0] = clock64();
-                mbar_wait(tempty, (uint32_t)((it & 1) ^ 1));     // the epilogue has read the previous tile out of TMEM
-                tc_fence_after();
-                if (P.dbg && blockIdx.x == 0 && it < 6) P.dbg[it * 8 + 1] = clock64();
                 for (int kb = 0; kb < nkb; kb++) {
                     mbar_wait(&bfull[sb], pb);
                     tc_fence_after();
                     const uint32_t bbase = smem_u32(sB + sb * bstage);
-                    for (int k = 0; k < ns; k++) {
+                    for (int k = ns - 1; k >= 0; k--) {
                         mbar_wait(&afull[sa], pa);
+                        if (kb == 0) {
+                            mbar_wait(&tempty[k], (uint32_t)((it & 1) ^ 1));   // the epilogue has read group k of the previous tile
+                            if (k == ns - 1 && P.dbg && blockIdx.x == 0 && it < 6) P.dbg[it * 8 + 1] = clock64();
+                        }
                         tc_fence_after();
                         const uint32_t a0 = smem_u32(sA + sa * AR_A_BYTES);
                         // The B slices l = 0..ns-1-k of this K block lie back to back in shared memory (64 rows x 128 B each),
                         // i.e. they ARE one K-major tile of (ns-k)*64 rows, and their groups k+l are adjacent TMEM column
                         // blocks: one MMA with N = 64*cnt multiplies A_k with cnt slices at once.  A 128-row MMA costs the
                         // same ~128 cycles for any N <= 256, so stacking cuts the 28 slice-pair MMAs per K block to 10.
+                        // The first touch of group g is (kb = 0, k = g, l = 0) and has to overwrite: in the first K block that
+                        // pair gets an MMA of its own (N = 64), the stacked MMAs start at l = 1.
                         const int lstep = P.stack ? 4 : 1;
-                        for (int l = 0; l < ns - k; l += lstep) {
+                        int l = 0;
+                        if (kb == 0) {
+                            const uint32_t idesc_1 = make_idesc_i8(BM, AR_BN);
+                            const uint32_t tacc = tmem_base + k * AR_BN;
+                            uint32_t acc = 0;
+#pragma unroll
+                            for (int kk = 0; kk < BK / UK; kk++) {
+                                mma_i8(tacc, make_desc_k_sw128(a0 + kk * UK), make_desc_k_sw128(bbase + kk * UK), idesc_1, acc);
+                                acc = 1;
+                            }
+                            l = 1;
+                        }
+                        for (; l < ns - k; l += lstep) {
                             const int cnt = (ns - k - l < lstep) ? ns - k - l : lstep;
                             const uint32_t idesc_n = make_idesc_i8(BM, cnt * AR_BN);
                             const uint32_t b0 = bbase + l * AR_B1_BYTES;
                             const uint32_t tacc = tmem_base + (k + l) * AR_BN;
-                            uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;   // first touch of group k+l is (kb=0, k=0)
 #pragma unroll
-                            for (int kk = 0; kk < BK / UK; kk++) {
-                                mma_i8(tacc, make_desc_k_sw128(a0 + kk * UK), make_desc_k_sw128(b0 + kk * UK), idesc_n, acc);
-                                acc = 1;
-                            }
+                            for (int kk = 0; kk < BK / UK; kk++)
+                                mma_i8(tacc, make_desc_k_sw128(a0 + kk * UK), make_desc_k_sw128(b0 + kk * UK), idesc_n, 1u);
                         }
                         mma_commit(&aempty[sa]);
                         if (++sa == nsa) { sa = 0; pa ^= 1; }
@@ -430,37 +466,52 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
             mbar_wait(tfull, (uint32_t)(it & 1));
             tc_fence_after();
             if (stamp) P.dbg[it * 8 + 4] = clock64();   // accumulators complete
+            // combine the groups in fp64, smallest weight first, row = this lane, all 64 columns; every group is handed back to
+            // the MMA warp as soon as its loads have landed
+            double accv[AR_BN];
+#pragma unroll
+            for (int j = 0; j < AR_BN; j++) accv[j] = 0.0;
+            const bool on0 = nt * AR_BN < P.N, on1 = nt * AR_BN + 32 < P.N;
 #pragma unroll 1
-            for (int c0 = 0; c0 < AR_BN; c0 += 32) {
-                const bool chunk_on = nt * AR_BN + c0 < P.N;
-                // combine the groups in fp64 (smallest weight first), row = this lane
-                double accv[32];
+            for (int g = ns - 1; g >= 0; g--) {
+                uint32_t r0[32], r1[32];
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + g * AR_BN;
+                if (on0) tmem_ld_32x32b_x32_nowait(ta, r0);
+                if (on1) tmem_ld_32x32b_x32_nowait(ta + 32, r1);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[g]);
+                const double w = pow2i(-12 - 7 * g);
+                if (on0) {
 #pragma unroll
-                for (int j = 0; j < 32; j++) accv[j] = 0.0;
-                if (chunk_on) {
-                    for (int g = ns - 1; g >= 0; g--) {
-                        uint32_t r[32];
-                        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + g * AR_BN + c0, r);
-                        const double w = pow2i(-12 - 7 * g);
+                    for (int j = 0; j < 32; j++) accv[j] += i2d_exact(r0[j]) * w;
+                }
+                if (on1) {
 #pragma unroll
-                        for (int j = 0; j < 32; j++) accv[j] += (double)(int)r[j] * w;
+                    for (int j = 0; j < 32; j++) accv[32 + j] += i2d_exact(r1[j]) * w;
+                }
+            }
+            if (stamp) P.dbg[it * 8 + 5] = clock64();   // TMEM handed back
+            // lane = output row (the TMEM lane): its 64 columns are contiguous in C, so every lane streams its own 512 B;
+            // the partial sectors of neighbouring stores merge in L2.  No transpose, no shuffles; the column exponents come
+            // through the read-only path, so they are not ordered behind the stores of the previous row.
+            if (mlane < P.M) {
+                const int nb = nt * AR_BN;
+                double* dst = P.C + off_lane + nb;
+                if (((P.N | P.ldc) & 3) == 0 && nb + AR_BN <= P.N) {
+                    // every row segment starts on a 32-byte boundary: 256-bit stores, one full sector per lane and instruction
+                    // (scalar stores leave 32 eight-byte fragments per instruction for L2 to merge)
+#pragma unroll
+                    for (int j = 0; j < AR_BN; j += 4) {
+                        const int4 eb = __ldg(reinterpret_cast<const int4*>(P.Eb + nb + j));
+                        const double v0 = accv[j] * pow2i(ea_lane + eb.x), v1 = accv[j + 1] * pow2i(ea_lane + eb.y);
+                        const double v2 = accv[j + 2] * pow2i(ea_lane + eb.z), v3 = accv[j + 3] * pow2i(ea_lane + eb.w);
+                        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "d"(v0), "d"(v1), "d"(v2), "d"(v3) : "memory");
                     }
-                }
-                if (c0 + 32 >= AR_BN) {   // last read of this tile's accumulators: hand TMEM back before the stores
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty);
-                    if (stamp) P.dbg[it * 8 + 5] = clock64();   // TMEM handed back
-                }
-                if (!chunk_on) continue;
-                // lane = output row (the TMEM lane): its 32 columns are contiguous in C, so every lane streams its own 256 B;
-                // the partial sectors of neighbouring stores merge in L2.  No transpose, no shuffles; the column exponents come
-                // through the read-only path, so they are not ordered behind the stores of the previous row/chunk.
-                if (mlane < P.M) {
-                    const int nb = nt * AR_BN + c0;
-                    double* dst = P.C + off_lane + nb;
+                } else {
 #pragma unroll
-                    for (int j = 0; j < 32; j++)
+                    for (int j = 0; j < AR_BN; j++)
                         if (nb + j < P.N) dst[j] = accv[j] * pow2i(ea_lane + __ldg(P.Eb + nb + j));
                 }
             }
