@@ -995,6 +995,8 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
                 // int32 accumulation bound: pairs(<=ns) * K * 64*64 < 2^31
                 int kmax = (int)((1L << 19) / d->k_slices);
                 kb = std::max(1, std::min(kb, kmax / ncol));
+                // stage 1 contracts over nao with tensor digits up to 127 (split_packed_kernel) against balanced digits (<= 64)
+                if ((long)nao * d->k_slices * 127 * 64 >= (1L << 31)) throw std::runtime_error("nao too large for the int32 accumulators of DF-K stage 1");
                 if ((size_t)kb * ncol * nao > d->y2_cap) { dev_free(d->d_Y2); d->y2_cap = (size_t)kb * ncol * nao; d->d_Y2 = (double*)dev_alloc(d->y2_cap * 8); }
                 if ((size_t)ncol * nao > d->occT_cap) { dev_free(d->d_occT); d->occT_cap = (size_t)ncol * nao; d->d_occT = (double*)dev_alloc(d->occT_cap * 8); }
                 if (!d->d_rowexp) {

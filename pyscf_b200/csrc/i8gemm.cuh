@@ -671,20 +671,44 @@ __global__ void __launch_bounds__(256) split_packed_kernel(const double* __restr
             int e = ex[r];
             if (e == EXP_NONE) e = 0;
             if (tcol == 0 && c4 == 0) E[orow0 + r] = e;
-            const double sc = pow2i(6 - e);
-            double rr[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) rr[j] = (pass ? S[c4 + j][rl] : S[rl][c4 + j]) * sc;
             int8_t* dst = out + (orow0 + r) * Kp + tcol * PT + c4;
-            for (int s_ = 0; s_ < ns; s_++) {
-                unsigned pack = 0;
+            if (ns <= 7) {
+                // One FP64 operation per element instead of four per digit: N = rint(x 2^(6-e+7(ns-1))) (|N| < 2^48) sits in the
+                // mantissa of x*scale + 1.5*2^52; its digits come out with integer shifts: the top one signed (-64..64), the others
+                // 0..127 (two's-complement style, no carries).  Still an exact representation; the digit products of stage 1 are
+                // bounded by 127*64 instead of 64*64, which the int32 accumulation bound covers up to K = nao < 37 000.
+                const double scN = pow2i(6 - e + 7 * (ns - 1));
+                long long N[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const double qv = rint(rr[j]);
-                    pack |= (unsigned)(unsigned char)(int8_t)(int)qv << (8 * j);
-                    rr[j] = (rr[j] - qv) * 128.0;
+                    const double t_ = fma(pass ? S[c4 + j][rl] : S[rl][c4 + j], scN, 6755399441055744.0);
+                    N[j] = (long long)(__double_as_longlong(t_) & 0x000FFFFFFFFFFFFFLL) - (1LL << 51);
                 }
-                *reinterpret_cast<unsigned*>(dst + (long)s_ * Rp * Kp) = pack;
+                for (int s_ = 0; s_ < ns; s_++) {
+                    const int sh = 7 * (ns - 1 - s_);
+                    unsigned pack = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int d_ = s_ == 0 ? (int)(N[j] >> sh) : (int)((N[j] >> sh) & 127);
+                        pack |= (unsigned)(d_ & 0xff) << (8 * j);
+                    }
+                    *reinterpret_cast<unsigned*>(dst + (long)s_ * Rp * Kp) = pack;
+                }
+            } else {
+                const double sc = pow2i(6 - e);
+                double rr[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) rr[j] = (pass ? S[c4 + j][rl] : S[rl][c4 + j]) * sc;
+                for (int s_ = 0; s_ < ns; s_++) {
+                    unsigned pack = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const double qv = rint(rr[j]);
+                        pack |= (unsigned)(unsigned char)(int8_t)(int)qv << (8 * j);
+                        rr[j] = (rr[j] - qv) * 128.0;
+                    }
+                    *reinterpret_cast<unsigned*>(dst + (long)s_ * Rp * Kp) = pack;
+                }
             }
         }
     }
