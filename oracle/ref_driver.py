@@ -48,6 +48,21 @@ def set_threads(n):
     return int(orc.oracle_omp_max_threads())
 
 
+def q_cond(mol, omega=None):
+    """The reference's own CVHFnr_int2e_q_cond (pyscf/lib/vhf/optimizer.c:408-454, compiled in place) on the oracle's int2e_sph."""
+    ref, orc = lib(), O.lib()
+    atm = np.ascontiguousarray(mol._atm, dtype=np.int32)
+    bas = np.ascontiguousarray(mol._bas, dtype=np.int32)
+    env = np.array(mol._env, dtype=np.float64)
+    env[8] = 0.0 if omega is None else omega
+    ao_loc = np.ascontiguousarray(mol.ao_loc_nr(cart=False), dtype=np.int32)
+    q = np.empty((len(bas), len(bas)))
+    ref.CVHFnr_int2e_q_cond(_fptr(orc, 'int2e_sph'), None, q.ctypes.data_as(ctypes.c_void_p), ao_loc.ctypes.data_as(ctypes.c_void_p),
+                            atm.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(len(atm)), bas.ctypes.data_as(ctypes.c_void_p),
+                            ctypes.c_int(len(bas)), env.ctypes.data_as(ctypes.c_void_p))
+    return q
+
+
 def get_jk(mol, dm, hermi=1, direct_scf_tol=1e-13, omega=None, screen=True, sample_stride=0, info=None):
     """J, K through CVHFnr_direct_drv (reference C) for real dm [..., nao, nao].
 

@@ -109,6 +109,7 @@ extern "C" int b200jk_create(b200jk_handle* out, const int32_t* atm, int natm, c
         h->d_sph_sh = upload(sph_sh); h->d_sph_m = upload(sph_m);
         h->d_sh_l = upload(sh_l); h->d_sh_cart = upload(sh_cart); h->d_sh_sph = upload(sh_sph);
         h->d_c2s = upload(c2s); h->d_c2s_off = upload(c2s_off);
+        for (int l = 0; l <= LMAX; l++) h->c2s_off[l] = c2s_off[l];
 
         // ---- Rys tables
         {
@@ -126,6 +127,7 @@ extern "C" int b200jk_create(b200jk_handle* out, const int32_t* atm, int natm, c
             h->tb.cheb = h->d_rys + cheb_off;
         }
 
+        const double expcutoff = (nenv > 0) ? env[0] : 0.0;
         // ---- shell pairs and primitive pairs per class
         for (int la = 0; la <= LAO_MAX; la++)
             for (int lb = 0; lb <= la; lb++) { h->pc[pair_class_id(la, lb)].la = la; h->pc[pair_class_id(la, lb)].lb = lb; }
@@ -144,6 +146,9 @@ extern "C" int b200jk_create(b200jk_handle* out, const int32_t* atm, int natm, c
                         double ea = a.e[pa], eb = b.e[pb], p = ea + eb;
                         double cc = a.c[pa] * b.c[pb] * std::exp(-ea * eb / p * r2);
                         if (std::fabs(cc) < PRIM_CUT) continue;
+                        // env[PTR_EXPCUTOFF] (slot 0, pyscf/gto/mole.py:58-88, :3065-3078): the caller's cutoff on the Gaussian-product
+                        // exponent of a primitive pair; 0 = library default (here: the coefficient-aware PRIM_CUT above)
+                        if (expcutoff > 0.0 && ea * eb / p * r2 > expcutoff) continue;
                         PrimPair pp;
                         pp.p = p;
                         pp.Px = (ea * a.r[0] + eb * b.r[0]) / p; pp.Py = (ea * a.r[1] + eb * b.r[1]) / p; pp.Pz = (ea * a.r[2] + eb * b.r[2]) / p;
@@ -205,8 +210,17 @@ extern "C" int b200jk_set_screening(b200jk_handle h, double tol, double omega)
         for (int c = 0; c < NPC; c++) {
             PairClass& P = h->pc[c];
             if (P.all.empty()) continue;
-            SchwarzFn fn{P.d_all, h->d_prims, h->tb, omega, P.la, P.lb};
-            launch_1d((long)P.all.size(), fn);
+            // the reference's bound: normalised real-spherical functions (exact for every l, optimizer.c:408-454)
+            const long ne = (long)ncart(P.la) * ncart(P.lb);
+            const long chunk = std::max<long>(1, (256L << 20) / (ne * ne * 8));     // <= 256 MB of scratch per launch
+            double* scratch = (double*)dev_alloc((size_t)std::min<long>(chunk, (long)P.all.size()) * ne * ne * 8);
+            for (long i0 = 0; i0 < (long)P.all.size(); i0 += chunk) {
+                long n = std::min<long>(chunk, (long)P.all.size() - i0);
+                SchwarzSphFn fn{P.d_all + i0, h->d_prims, h->tb, omega, P.la, P.lb, h->d_c2s + h->c2s_off[P.la], h->d_c2s + h->c2s_off[P.lb], scratch};
+                launch_1d(n, fn);
+                dev_sync();
+            }
+            dev_free(scratch);
         }
         dev_sync();
         for (int c = 0; c < NPC; c++) {
@@ -255,10 +269,9 @@ extern "C" int b200jk_get_q_cond(b200jk_handle h, double* q, int nbas)
     for (int c = 0; c < NPC; c++)
         for (auto& sp : h->pc[c].all) {
             int I = h->ref_shell_of[sp.ish], J = h->ref_shell_of[sp.jsh];
-            // device bounds are over bare Cartesian monomials; rescale to the reference's normalised AOs
-            // (exact for s and p, where cart->sph is a multiple of the identity; an estimate for l >= 2)
-            auto fl = [](int l) { auto T = make_c2s(l); double m = 0; for (double t : T) m = std::max(m, std::fabs(t)); return m; };
-            double v = std::max(sp.q * fl(h->sh[sp.ish].l) * fl(h->sh[sp.jsh].l), 1e-100);
+            // device bounds are already in the reference's normalisation (spherical, SchwarzSphFn); a general-contracted
+            // reference shell takes the maximum over its segments, as CVHFnr_int2e_q_cond does over its nctr blocks
+            double v = std::max(sp.q, 1e-100);
             q[(long)I * nbas + J] = std::max(q[(long)I * nbas + J], v);
             q[(long)J * nbas + I] = std::max(q[(long)J * nbas + I], v);
         }
@@ -308,7 +321,8 @@ static int direct_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, 
             }
             dmk = h->d_dmk;
         }
-        DmCondFn dc{vj ? h->d_dmj : nullptr, n_dm, vk ? dmk : nullptr, n_dm_k, h->d_dmc, h->nsh, h->ncart, h->d_sh_l, h->d_sh_cart};
+        // dm_cond on the spherical input, the reference's definition (the Schwarz bounds are spherical too)
+        DmCondSphFn dc{dsph, n_dm, h->d_dmc, h->nsh, h->nsph, h->d_sh_l, h->d_sh_sph};
         launch_1d((long)h->nsh * h->nsh, dc, st); launches++;
         if (vj) dev_zero(h->d_vj, nc2 * n_dm * 8, st);
         if (vk) dev_zero(h->d_vk, nc2 * n_dm_k * 8, st);

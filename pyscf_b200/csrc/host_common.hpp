@@ -191,6 +191,15 @@ struct SchwarzFn {
     ShellPair* pairs; const PrimPair* prims; RysTables tb; double omega; int la, lb;
     B2_HD void operator()(long i) const { pairs[i].q = schwarz_pair(la, lb, pairs[i], prims, tb, omega); }
 };
+// the reference's Schwarz bound (normalised real-spherical functions); scratch: (ncart(la) ncart(lb))^2 doubles per pair
+struct SchwarzSphFn {
+    ShellPair* pairs; const PrimPair* prims; RysTables tb; double omega; int la, lb; const double *Ta, *Tb; double* scratch;
+    B2_HD void operator()(long i) const
+    {
+        const long ne = (long)((la + 1) * (la + 2) / 2) * ((lb + 1) * (lb + 2) / 2);
+        pairs[i].q = schwarz_pair_sph(la, lb, pairs[i], prims, tb, omega, Ta, Tb, scratch + i * ne * ne);
+    }
+};
 
 // D_cart[s][mu][nu] = sum_{m,m'} T[m,mu] Dsym[m,m'] T[m',nu]; mode 0: (D+D^T)/2, 1: (D-D^T)/2, 2: D as is
 struct Sph2CartFn {
@@ -254,6 +263,27 @@ struct Cart2SphFn {
             }
         }
         if (accumulate) osph[idx] += acc; else osph[idx] = acc;
+    }
+};
+
+// dm_cond as the reference defines it (CVHFnr_dm_cond, pyscf/lib/vhf/optimizer.c:494-518): (|D_mn| + |D_nm|)/2 maximised over the
+// SPHERICAL block of the two (device) shells and over all density matrices — the scale the spherical Schwarz bounds live on
+struct DmCondSphFn {
+    const double* dsph; int nd; double* dmc; int nsh, nsph; const int *sh_l, *sh_sph;
+    B2_HD void operator()(long idx) const
+    {
+        int i = (int)(idx / nsh), j = (int)(idx - (long)i * nsh);
+        int ni = 2 * sh_l[i] + 1, nj = 2 * sh_l[j] + 1;
+        double m = 0.0;
+        for (int s = 0; s < nd; s++) {
+            const double* D = dsph + (size_t)s * nsph * nsph;
+            for (int a = 0; a < ni; a++)
+                for (int b = 0; b < nj; b++) {
+                    double v = 0.5 * (fabs(D[(size_t)(sh_sph[i] + a) * nsph + sh_sph[j] + b]) + fabs(D[(size_t)(sh_sph[j] + b) * nsph + sh_sph[i] + a]));
+                    m = v > m ? v : m;
+                }
+        }
+        dmc[idx] = m;
     }
 };
 

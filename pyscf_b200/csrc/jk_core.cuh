@@ -632,4 +632,105 @@ B2_HD double schwarz_pair(int la, int lb, const ShellPair& sp, const PrimPair* p
     return sqrt(m);
 }
 
+// The same bound in the REFERENCE's normalisation: q = sqrt(max_{A,B} |(AB|AB)|) over the real-spherical functions A of shell a
+// and B of shell b, exactly what CVHFnr_int2e_q_cond (pyscf/lib/vhf/optimizer.c:408-454) takes from int2e_sph.  The Cartesian
+// block M[ab][a'b'] = (ab|a'b') is accumulated over primitives and roots, then every spherical pair is u^T M u with
+// u = T_a[A,:] (x) T_b[B,:] (T = the cart->sph matrices the density / J,K transforms use).  Setup only: one thread per shell pair,
+// M in thread-local memory (100 x 100 doubles for an (ff| pair).
+B2_HD double schwarz_pair_sph(int la, int lb, const ShellPair& sp, const PrimPair* prims, const RysTables& tb, double omega,
+                              const double* Ta, const double* Tb, double* M)
+{
+    const int L = la + lb, nr = L + 1;
+    const int na = ncart(la), nb = ncart(lb), ne = na * nb;
+    for (int e = 0; e < ne * ne; e++) M[e] = 0.0;
+    const double AB[3] = {sp.ABx, sp.ABy, sp.ABz};
+    for (int ip = 0; ip < sp.nprim; ip++)
+        for (int kp = 0; kp < sp.nprim; kp++) {
+            const PrimPair& bp = prims[sp.prim_off + ip];
+            const PrimPair& kq = prims[sp.prim_off + kp];
+            double p = bp.p, q = kq.p, pq = p + q, ipq = 1.0 / pq;
+            double PQ[3] = {bp.Px - kq.Px, bp.Py - kq.Py, bp.Pz - kq.Pz};
+            double PA[3] = {bp.PAx, bp.PAy, bp.PAz}, QC[3] = {kq.PAx, kq.PAy, kq.PAz};
+            double rho = p * q * ipq;
+            const double x0 = rho * (PQ[0] * PQ[0] + PQ[1] * PQ[1] + PQ[2] * PQ[2]), pref0 = bp.cc * kq.cc / sqrt(pq);
+            for (int r2 = 0; r2 < (omega < 0.0 ? 2 * nr : nr); r2++) {
+                const int r = r2 % nr;
+                double theta = 1.0, x = x0, pref = pref0;
+                const double om = (omega < 0.0) ? (r2 >= nr ? -omega : 0.0) : omega;
+                if (om > 0.0) { theta = om * om / (om * om + rho); x *= theta; pref *= sqrt(theta); }
+                if (r2 >= nr) pref = -pref;
+                double u, w;
+                rys_root(tb, nr, r, x, u, w);
+                u *= theta; w *= pref;
+                double I[3][2 * LMAX + 1][2 * LMAX + 1];
+                double b00 = 0.5 * u * ipq, b10 = (1.0 - u * q * ipq) * 0.5 / p, b01 = (1.0 - u * p * ipq) * 0.5 / q;
+                // G[d][(i*(lb+1)+j)*nij + (i'*(lb+1)+j')] = 2-D integral of direction d with bra powers (i,j), ket powers (i',j')
+                double G[3][16 * 16];
+                const int nij = (la + 1) * (lb + 1);
+                for (int d = 0; d < 3; d++) {
+                    double c00 = PA[d] - u * q * ipq * PQ[d], c0p = QC[d] + u * p * ipq * PQ[d];
+                    I[d][0][0] = (d == 2) ? w : 1.0;
+                    if (L > 0) I[d][1][0] = c00 * I[d][0][0];
+                    for (int n = 1; n < L; n++) I[d][n + 1][0] = c00 * I[d][n][0] + n * b10 * I[d][n - 1][0];
+                    for (int m = 0; m < L; m++)
+                        for (int n = 0; n <= L; n++) {
+                            double val = c0p * I[d][n][m];
+                            if (m > 0) val += m * b01 * I[d][n][m - 1];
+                            if (n > 0) val += n * b00 * I[d][n - 1][m];
+                            I[d][n][m + 1] = val;
+                        }
+                    for (int i = 0; i <= la; i++)
+                        for (int j = 0; j <= lb; j++)
+                            for (int i2 = 0; i2 <= la; i2++)
+                                for (int j2 = 0; j2 <= lb; j2++) {
+                                    double gsum = 0.0, bs = 1.0;
+                                    for (int s_ = 0; s_ <= j; s_++) {
+                                        double ps = 1.0;
+                                        for (int e = 0; e < j - s_; e++) ps *= AB[d];
+                                        double bt = 1.0;
+                                        for (int t_ = 0; t_ <= j2; t_++) {
+                                            double pt = 1.0;
+                                            for (int e = 0; e < j2 - t_; e++) pt *= AB[d];
+                                            gsum += bs * ps * bt * pt * I[d][i + s_][i2 + t_];
+                                            bt = bt * (j2 - t_) / (t_ + 1);
+                                        }
+                                        bs = bs * (j - s_) / (s_ + 1);
+                                    }
+                                    G[d][(i * (lb + 1) + j) * nij + i2 * (lb + 1) + j2] = gsum;
+                                }
+                }
+                for (int b = 0; b < nb; b++)
+                    for (int a = 0; a < na; a++) {
+                        const int ax = cart_px(la, a), ay = cart_py(la, a), az = la - ax - ay;
+                        const int bx = cart_px(lb, b), by = cart_py(lb, b), bz = lb - bx - by;
+                        const int rx = (ax * (lb + 1) + bx) * nij, ry = (ay * (lb + 1) + by) * nij, rz = (az * (lb + 1) + bz) * nij;
+                        double* Mrow = M + (size_t)(b * na + a) * ne;
+                        for (int b2 = 0; b2 < nb; b2++)
+                            for (int a2 = 0; a2 < na; a2++) {
+                                const int cx = cart_px(la, a2), cy = cart_py(la, a2), cz = la - cx - cy;
+                                const int dx = cart_px(lb, b2), dy = cart_py(lb, b2), dz = lb - dx - dy;
+                                Mrow[b2 * na + a2] += G[0][rx + cx * (lb + 1) + dx] * G[1][ry + cy * (lb + 1) + dy] * G[2][rz + cz * (lb + 1) + dz];
+                            }
+                    }
+            }
+        }
+    double best = 0.0;
+    for (int A = 0; A < 2 * la + 1; A++)
+        for (int B = 0; B < 2 * lb + 1; B++) {
+            double val = 0.0;
+            for (int b = 0; b < nb; b++)
+                for (int a = 0; a < na; a++) {
+                    const double ue = Ta[A * na + a] * Tb[B * nb + b];
+                    if (ue == 0.0) continue;
+                    const double* Mrow = M + (size_t)(b * na + a) * ne;
+                    double acc = 0.0;
+                    for (int b2 = 0; b2 < nb; b2++)
+                        for (int a2 = 0; a2 < na; a2++) acc += Mrow[b2 * na + a2] * Ta[A * na + a2] * Tb[B * nb + b2];
+                    val += ue * acc;
+                }
+            best = fmax(best, fabs(val));
+        }
+    return sqrt(best);
+}
+
 }  // namespace b200jk

@@ -152,7 +152,26 @@ def test_emulated_screening_and_errors(emu_lib):
     q = opt.q_cond
     qo = O.q_cond(mol)
     big = qo > 1e-12  # negligible pairs are dropped on the device side (reported as the 1e-100 floor)
-    assert q.shape == qo.shape and abs(np.log(q[big] / qo[big])).max() < 1e-9  # s,p: identical to CVHFnr_int2e_q_cond
+    assert q.shape == qo.shape and abs(np.log(q[big] / qo[big])).max() < 1e-9  # identical to CVHFnr_int2e_q_cond
+
+
+def test_q_cond_is_the_reference_bound_for_d_and_f_shells(emu_lib):
+    """b200jk_get_q_cond == CVHFnr_int2e_q_cond (pyscf/lib/vhf/optimizer.c:408-454) for every angular momentum: the device
+    bounds are over the normalised real-spherical functions, general contractions take the maximum over their segments.
+    Checked against the oracle's restatement and, when oracle/_ref is built, against the reference's own C routine."""
+    mol = gto.M(atom='O 0 0 0; H 0 -0.757 0.587; H 0.3 0.757 0.587', basis='cc-pvtz')
+    assert int(mol._bas[:, 1].max()) == 3
+    opt = VHFOpt(mol, libpath=emu_lib)
+    q = opt.q_cond
+    qo = O.q_cond(mol)
+    assert abs(np.log(q / qo)).max() < 1e-9
+    from oracle import ref_driver as R
+    if R.available():
+        qr = R.q_cond(mol)
+        assert abs(np.log(q / qr)).max() < 1e-9
+    # erf-attenuated operator
+    opt = VHFOpt(mol, omega=0.4, libpath=emu_lib)
+    assert abs(np.log(opt.q_cond / O.q_cond(mol, omega=0.4))).max() < 1e-9
 
 
 def test_emulated_experimental_layouts(emu_lib, emu_lib_experimental):

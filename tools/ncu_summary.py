@@ -23,7 +23,10 @@ KEYS = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__block
         'smsp__average_warps_issue_stalled_membar_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
-        'l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum', 'lts__t_sectors_op_red.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_red.sum']
+        'l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum', 'lts__t_sectors_op_red.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_red.sum',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_tensor.sum',
+        'sm__pipe_tensor_op_imma_cycles_active.avg.pct_of_peak_sustained_active', 'sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active',
+        'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_bytes.sum', 'sm__cycles_elapsed.max']
 for path in sys.argv[1:]:
     rows = list(csv.reader(open(path)))
     hdr = rows[0]
