@@ -424,15 +424,15 @@ def measure(args, rank, world, dist):
         for k in ('k_gemm1', 'k_gemm2'):
             ms_k, n_k = stg[k]
             if n_k:
-                stages[k] = {'kernel': 'i8gemm_ar_kernel' if k == 'k_gemm1' else 'i8gemm_kernel', 'bound': 'tensor',
+                stages[k] = {'kernel': 'i8gemm_ar_kernel (stage 1: Y = A C~)' if k == 'k_gemm1' else 'i8gemm_ar_kernel (stage 2: K += Y Y^T, accumulate mode)', 'bound': 'tensor',
                              'launches_per_step': n_k, 'ms_per_launch': ms_k / n_k, 'ms_per_step': ms_k,
                              'alg_int8_ops_per_launch': half_ops / n_k, 'achieved': half_ops / (ms_k * 1e-3) / 1e12,
                              'peak': tensor_peak, 'unit': 'TOP/s (int8)', 'frac': half_ops / (ms_k * 1e-3) / 1e12 / tensor_peak}
                 if k == 'k_gemm2':
-                    # the kernel computes only the 128 x 256 tiles that touch the upper triangle of the symmetric product
-                    mt_, nt_ = (nao + 127) // 128, (nao + 255) // 256
-                    done = sum(1 for a in range(mt_) for b in range(nt_) if not (b + 1) * 256 <= a * 128)
-                    fexec = done * 128.0 * 256.0 / (nao * nao)
+                    # the kernel computes only the 128 x 64 tiles that touch the upper triangle of the symmetric product
+                    mt_, nt_ = (nao + 127) // 128, (nao + 63) // 64
+                    done = sum(max(0, nt_ - 2 * a) for a in range(mt_))
+                    fexec = done * 128.0 * 64.0 / (nao * nao)
                     stages[k].update({'executed_frac_of_alg_ops': fexec, 'achieved_executed': stages[k]['achieved'] * fexec,
                                       'frac_executed': stages[k]['frac'] * fexec,
                                       'note': 'algorithmic count = the full Y Y^T product of the reference dgemm (SURVEY 8d); the kernel executes '

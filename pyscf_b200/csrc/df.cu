@@ -1080,7 +1080,9 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
                         tick(2);
                         mark(B200JK_DF_STAGE_K_GEMM2);
                         // K += Y Y^T (orbitals) or Y G^T (general density; only its upper triangle when D, hence K, is symmetric)
-                        i8g::gemm(d->SY, use_occ ? d->SY : d->SG, d->d_vk + (size_t)s * n2, nao, 0, k_sym, st);
+                        static const bool old_g2 = getenv("B200JK_G2_OLD") != nullptr;   // yardstick: the round-1 stage-2 kernel
+                        if (old_g2) i8g::gemm(d->SY, use_occ ? d->SY : d->SG, d->d_vk + (size_t)s * n2, nao, 0, k_sym, st);
+                        else i8g::gemm_ar_acc(d->SY, use_occ ? d->SY : d->SG, d->d_vk + (size_t)s * n2, nao, k_sym, st);
                         mark(-1);
                         tick(3);
                         if (prof && r0 + kb >= r_hi) {

@@ -139,6 +139,7 @@ void gemm_ar(const SliceStack& A, int a_row0, int M, const SliceStack& B, double
     P.stack = stack;
     P.nsa = nsa;
     const int ntiles = ((B.R + AR_BN - 1) / AR_BN) * ((M + BM - 1) / BM);
+    P.ar_ntiles = ntiles; P.ar_ksplit = 1; P.ar_kb_per = A.Kp / BK; P.accumulate = 0;
     static const int persist = getenv("B200JK_AR_PERSIST") ? atoi(getenv("B200JK_AR_PERSIST")) : 1;   // 0: one tile per CTA (yardstick)
     dim3 grid(persist ? std::min(ntiles, nsm) : ntiles);
     static const bool dbg = getenv("B200JK_I8_DEBUG") != nullptr;   // cycle stamps of CTA 0 (tuning)
@@ -160,6 +161,55 @@ void gemm_ar(const SliceStack& A, int a_row0, int M, const SliceStack& B, double
                     hd[it * 8 + 1] - hd[it * 8 + 0], hd[it * 8 + 2] - hd[it * 8 + 1], hd[it * 8 + 4] - hd[it * 8 + 3],
                     hd[it * 8 + 5] - hd[it * 8 + 4], hd[it * 8 + 6] - hd[it * 8 + 5], it ? hd[it * 8 + 6] - hd[(it - 1) * 8 + 6] : 0LL);
     }
+    CK(cudaGetLastError());
+}
+
+// C += A B^T (upper triangle only when symmetric) on the A-stationary kernel with all slice-pair groups resident in TMEM
+// (i8gemm_ar_kernel): stage 2 of DF-K.  Against i8gemm_kernel's one (A_k, B_l) tile pair per pipeline stage this loads every
+// A slice tile once per K block and multiplies it with all its B slices: half the operand traffic per output column.
+// Work items = tiles x K ranges, sized to fill whole waves of the persistent grid.
+void gemm_ar_acc(const SliceStack& A, const SliceStack& B, double* C, long ldc, bool symmetric, cudaStream_t st)
+{
+    if (A.Kp != B.Kp || A.ns != B.ns) throw std::runtime_error("i8gemm_ar_acc: operand stacks disagree");
+    if (A.ns * AR_BN > 512) throw std::runtime_error("i8gemm_ar_acc: too many slices for TMEM");
+    static bool configured = false;
+    static int nsm = 148;
+    if (!configured) {
+        CK(cudaFuncSetAttribute(i8gemm_ar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM_MAX));
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+        configured = true;
+    }
+    int nsa = AR_MAXA;
+    while (nsa > 2 && ar_smem_bytes(nsa, A.ns) > AR_SMEM_MAX) nsa--;
+    CUtensorMap ta, tb;
+    make_tmap(&ta, A.q, (uint64_t)A.ns * A.Rp, A.Kp, BM);
+    make_tmap(&tb, B.q, (uint64_t)B.ns * B.Rp, B.Kp, AR_BN);
+    GemmParams P{};
+    P.M = A.R; P.N = B.R; P.Kp = A.Kp; P.Mp = A.Rp; P.Np = B.Rp; P.ns = A.ns; P.symmetric = symmetric ? 1 : 0;
+    P.Ea = A.E; P.Eb = B.E; P.C = C; P.ldc = ldc; P.inner = 0; P.a_row0 = 0; P.ksplit = 1; P.dbg = nullptr;
+    P.stack = 1; P.nsa = nsa; P.accumulate = 1;
+    const int ntm = (A.R + BM - 1) / BM, ntn = (B.R + AR_BN - 1) / AR_BN;
+    int tiles = 0;
+    for (int mt = 0; mt < ntm; mt++) tiles += symmetric ? std::max(0, ntn - (BM / AR_BN) * mt) : ntn;
+    if (symmetric && ntn < (BM / AR_BN) * (ntm - 1) + 1) throw std::runtime_error("i8gemm_ar_acc: symmetric product needs a square output");
+    const int nkb = A.Kp / BK;
+    // K ranges: >= 8 K blocks each; among those the count that wastes the least of the last wave of the persistent grid
+    int best = 1; double best_eff = -1.0;
+    for (int ks = 1; ks <= std::max(1, nkb / 8); ks++) {
+        const int per = (nkb + ks - 1) / ks, kse = (nkb + per - 1) / per;
+        const long items = (long)tiles * kse;
+        const double eff = (double)items / ((double)nsm * ((items + nsm - 1) / nsm));
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = kse; }
+        if (items > 12L * nsm) break;
+    }
+    P.ar_kb_per = (nkb + best - 1) / best;
+    P.ar_ksplit = (nkb + P.ar_kb_per - 1) / P.ar_kb_per;
+    P.ar_ntiles = tiles;
+    const long items = (long)tiles * P.ar_ksplit;
+    dim3 grid((unsigned)std::min<long>(items, nsm));
+    i8gemm_ar_kernel<<<grid, NTHREADS, ar_smem_bytes(nsa, A.ns), st>>>(ta, tb, P);
     CK(cudaGetLastError());
 }
 

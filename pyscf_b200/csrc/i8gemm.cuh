@@ -47,6 +47,9 @@ struct GemmParams {
     long long* dbg;        // optional cycle stamps of CTA (0,0) (tests/tuning)
     int stack;             // i8gemm_ar_kernel: multiply A_k with up to 4 stacked B slices per MMA (N = 256)
     int nsa;               // i8gemm_ar_kernel: depth of the A ring (host: as many 16 KB stages as fit in 227 KB)
+    // i8gemm_ar_kernel as stage 2 of DF-K (K += Y Y^T / Y G^T): work item = (tile, K range); ar_ksplit K ranges per tile,
+    // results meet in fp64 reductions (accumulate), only tiles touching the upper triangle when symmetric
+    int ar_ksplit, ar_kb_per, ar_ntiles, accumulate;
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -334,6 +337,27 @@ constexpr int AR_BAR_BYTES = 512, AR_EPI_BYTES = 0;   // the epilogue needs no s
 constexpr int AR_SMEM_MAX = 232448;              // 227 KB opt-in limit per CTA
 __host__ __device__ constexpr int ar_smem_bytes(int nsa, int ns) { return nsa * AR_A_BYTES + AR_NSB * ns * AR_B1_BYTES + AR_BAR_BYTES + AR_EPI_BYTES + 1024; }
 
+// work item -> (m tile, n tile, K-block range).  Items are numbered K range slowest, tile fastest (CTAs running side by side
+// share the A tile of their m tile in L2); symmetric: only the tiles with (nt + 1) * AR_BN > mt * BM, i.e. nt >= 2 mt.
+__device__ __forceinline__ void ar_decode_item(const GemmParams& P, int item, int ntn, int nkb, int& mt, int& nt, int& kb0, int& kb1)
+{
+    const int ks = item / P.ar_ntiles;
+    int tile = item - ks * P.ar_ntiles;
+    if (P.symmetric) {
+        mt = 0;
+        for (;;) {
+            const int cnt = ntn - (BM / AR_BN) * mt;
+            if (tile < cnt) break;
+            tile -= cnt; mt++;
+        }
+        nt = (BM / AR_BN) * mt + tile;
+    } else {
+        mt = tile / ntn; nt = tile - mt * ntn;
+    }
+    kb0 = ks * P.ar_kb_per;
+    kb1 = (kb0 + P.ar_kb_per < nkb) ? kb0 + P.ar_kb_per : nkb;
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const GemmParams P)
 {
@@ -355,7 +379,8 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = P.Kp / BK;
     const int ntn = (P.N + AR_BN - 1) / AR_BN, ntm = (P.M + BM - 1) / BM;
-    const int ntiles = ntn * ntm;
+    const int ntiles = P.ar_ntiles * P.ar_ksplit;     // work items
+    (void)ntm;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmapA);
@@ -379,8 +404,9 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
         if (lane == 0) {
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int mt = tile / ntn, nt = tile - mt * ntn;
-                for (int kb = 0; kb < nkb; kb++) {
+                int mt, nt, kb0, kb1;
+                ar_decode_item(P, tile, ntn, nkb, mt, nt, kb0, kb1);
+                for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait(&bempty[sb], pb ^ 1);
                     mbar_expect_tx(&bfull[sb], ns * AR_B1_BYTES);
                     for (int l = 0; l < ns; l++)
@@ -401,13 +427,15 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
             int it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
                 if (P.dbg && blockIdx.x == 0 && it < 6) P.dbg[it * 8 + 0] = clock64();
-                for (int kb = 0; kb < nkb; kb++) {
+                int mt_, nt_, kb0, kb1;
+                ar_decode_item(P, tile, ntn, nkb, mt_, nt_, kb0, kb1);
+                for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait(&bfull[sb], pb);
                     tc_fence_after();
                     const uint32_t bbase = smem_u32(sB + sb * bstage);
                     for (int k = ns - 1; k >= 0; k--) {
                         mbar_wait(&afull[sa], pa);
-                        if (kb == 0) {
+                        if (kb == kb0) {
                             mbar_wait(&tempty[k], (uint32_t)((it & 1) ^ 1));   // the epilogue has read group k of the previous tile
                             if (k == ns - 1 && P.dbg && blockIdx.x == 0 && it < 6) P.dbg[it * 8 + 1] = clock64();
                         }
@@ -421,7 +449,7 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
                         // pair gets an MMA of its own (N = 64), the stacked MMAs start at l = 1.
                         const int lstep = P.stack ? 4 : 1;
                         int l = 0;
-                        if (kb == 0) {
+                        if (kb == kb0) {
                             const uint32_t idesc_1 = make_idesc_i8(BM, AR_BN);
                             const uint32_t tacc = tmem_base + k * AR_BN;
                             uint32_t acc = 0;
@@ -455,7 +483,8 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
         const int q = warp & 3;
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-            const int mt = tile / ntn, nt = tile - mt * ntn;
+            int mt, nt, kb0_, kb1_;
+            ar_decode_item(P, tile, ntn, nkb, mt, nt, kb0_, kb1_);
             const int mrow0 = mt * BM + q * 32;
             // exponent and output offset of this warp's 32 rows, one row per lane, fetched once per tile (see i8gemm_kernel)
             const int mlane = mrow0 + lane;
@@ -496,7 +525,19 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
             // lane = output row (the TMEM lane): its 64 columns are contiguous in C, so every lane streams its own 512 B;
             // the partial sectors of neighbouring stores merge in L2.  No transpose, no shuffles; the column exponents come
             // through the read-only path, so they are not ordered behind the stores of the previous row.
-            if (mlane < P.M) {
+            if (P.accumulate) {
+                // partial result of this K range: fp64 reductions; every lane walks its own row, so the 32 reductions of one
+                // instruction go to 32 rows (scattered, but this epilogue runs once per 128 x 64 x K-range item)
+                if (mlane < P.M) {
+                    const int nb = nt * AR_BN;
+                    double* dst = P.C + off_lane + nb;
+#pragma unroll
+                    for (int j = 0; j < AR_BN; j++) {
+                        const int n = nb + j;
+                        if (n < P.N && (!P.symmetric || n >= mlane)) atomicAdd(dst + j, accv[j] * pow2i(ea_lane + __ldg(P.Eb + n)));
+                    }
+                }
+            } else if (mlane < P.M) {
                 const int nb = nt * AR_BN;
                 double* dst = P.C + off_lane + nb;
                 if (((P.N | P.ldc) & 3) == 0 && nb + AR_BN <= P.N) {

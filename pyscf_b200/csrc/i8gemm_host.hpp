@@ -20,6 +20,8 @@ void packed_rowexp(const double* cderi, long npair, int nao, int nr, int* rowexp
 void split_packed_into(SliceStack& S, int out_row0, const double* cderi, long npair, int nao, int nr, const int* rowexp, cudaStream_t st);
 void split_packed(SliceStack& S, const double* cderi, long npair, int nao, int nr, const int* rowexp, int ns, cudaStream_t st);
 void gemm_ar(const SliceStack& A, int a_row0, int M, const SliceStack& B, double* C, long ldc, int inner, cudaStream_t st);
+// C[m*ldc + n] += A B^T on the A-stationary all-groups-resident kernel (stage 2 of DF-K); upper triangle only when symmetric
+void gemm_ar_acc(const SliceStack& A, const SliceStack& B, double* C, long ldc, bool symmetric, cudaStream_t st);
 // C[m*ldc + n] (or the transposed scatter when inner>0, see GemmParams) += A B^T
 void gemm(const SliceStack& A, const SliceStack& B, double* C, long ldc, int inner, bool symmetric, cudaStream_t st,
           long long* dbg = nullptr);
