@@ -1073,10 +1073,15 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
                         tick(-1);
                         tick(0);
                         mark(B200JK_DF_STAGE_K_GEMM1);
-                        i8g::gemm_ar(d->SA, d->sa_persistent ? (r0 - r_lo) * nao : 0, nr * nao, d->SC, d->d_Y2, (long)nr * ncol, nao, st);
+                        // stage 1 leaves the row maxima of Y behind (GemmParams::rowmax): the slicing of Y is one pass
+                        const bool premax = (long)nr * ncol >= 8192;
+                        if (premax) i8g::split_rows_prepare(d->SY, nao, nr * ncol, d->k_slices, st);
+                        i8g::gemm_ar(d->SA, d->sa_persistent ? (r0 - r_lo) * nao : 0, nr * nao, d->SC, d->d_Y2, (long)nr * ncol, nao, st,
+                                     premax ? d->SY.maxbits : nullptr);
                         tick(1);
                         mark(B200JK_DF_STAGE_K_SLICE);
-                        i8g::split_rows(d->SY, d->d_Y2, (long)nr * ncol, nao, nr * ncol, d->k_slices, st);
+                        if (premax) i8g::split_rows_premax(d->SY, d->d_Y2, (long)nr * ncol, nao, nr * ncol, d->k_slices, st);
+                        else i8g::split_rows(d->SY, d->d_Y2, (long)nr * ncol, nao, nr * ncol, d->k_slices, st);
                         tick(2);
                         mark(B200JK_DF_STAGE_K_GEMM2);
                         // K += Y Y^T (orbitals) or Y G^T (general density; only its upper triangle when D, hence K, is symmetric)

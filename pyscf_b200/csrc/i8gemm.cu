@@ -52,6 +52,27 @@ void split_rows_into(SliceStack& S, int row0, const double* X, long ldx, int row
     CK(cudaGetLastError());
 }
 
+// first half of split_rows for a matrix that is still being produced: allocation + cleared row maxima, which the producer
+// (stage 1 of DF-K, GemmParams::rowmax) fills; split_rows_premax then cuts the slices without a row-maximum pass
+void split_rows_prepare(SliceStack& S, int rows, int k, int ns, cudaStream_t st)
+{
+    S.alloc(rows, k, ns);
+    CK(cudaMemsetAsync(S.maxbits, 0, (size_t)rows * 8, st));
+}
+void split_rows_premax(SliceStack& S, const double* X, long ldx, int rows, int k, int ns, cudaStream_t st)
+{
+    if (S.R != rows || S.K != k || S.ns != ns) throw std::runtime_error("split_rows_premax: call split_rows_prepare first");
+    if (S.Rp > rows) {
+        for (int s = 0; s < ns; s++)
+            CK(cudaMemsetAsync(S.q + ((size_t)s * S.Rp + rows) * S.Kp, 0, (size_t)(S.Rp - rows) * S.Kp, st));
+        CK(cudaMemsetAsync(S.E + rows, 0, (size_t)(S.Rp - rows) * 4, st));
+    }
+    const long seglen = 8192;
+    unsigned nseg = (unsigned)((S.Kp + seglen - 1) / seglen);
+    split_long_kernel<<<dim3(nseg, rows), 256, 0, st>>>(X, ldx, k, S.Rp, S.Kp, ns, seglen, S.maxbits, S.q, S.E);
+    CK(cudaGetLastError());
+}
+
 void split_rows(SliceStack& S, const double* X, long ldx, int rows, int k, int ns, cudaStream_t st)
 {
     S.alloc(rows, k, ns);
@@ -93,8 +114,12 @@ void split_packed_into(SliceStack& S, int out_row0, const double* cderi, long np
     const unsigned nt = (unsigned)(S.Kp / PT);
     for (int p0 = 0; p0 < nr; p0 += 32768) {
         int n = std::min(32768, nr - p0);
-        split_packed_kernel<<<dim3(nt, nt, n), 256, 0, st>>>(cderi + (size_t)p0 * npair, npair, nao, rowexp + (size_t)p0 * nao, S.ns, S.Rp, S.Kp,
-                                                             out_row0 + p0 * nao, S.q, S.E);
+        if (S.ns == 7)
+            split_packed_kernel<true><<<dim3(nt, nt, n), 256, 0, st>>>(cderi + (size_t)p0 * npair, npair, nao, rowexp + (size_t)p0 * nao, S.ns, S.Rp, S.Kp,
+                                                                       out_row0 + p0 * nao, S.q, S.E);
+        else
+            split_packed_kernel<false><<<dim3(nt, nt, n), 256, 0, st>>>(cderi + (size_t)p0 * npair, npair, nao, rowexp + (size_t)p0 * nao, S.ns, S.Rp, S.Kp,
+                                                                        out_row0 + p0 * nao, S.q, S.E);
     }
     CK(cudaGetLastError());
 }
@@ -112,7 +137,8 @@ void split_packed(SliceStack& S, const double* cderi, long npair, int nao, int n
 }
 
 // stage-1 GEMM of DF-K with all slice-pair groups resident in TMEM (i8gemm_ar_kernel): rows [a_row0, a_row0+M) of A
-void gemm_ar(const SliceStack& A, int a_row0, int M, const SliceStack& B, double* C, long ldc, int inner, cudaStream_t st)
+void gemm_ar(const SliceStack& A, int a_row0, int M, const SliceStack& B, double* C, long ldc, int inner, cudaStream_t st,
+             unsigned long long* rowmax)
 {
     if (A.Kp != B.Kp || A.ns != B.ns) throw std::runtime_error("i8gemm_ar: operand stacks disagree");
     if (A.ns * AR_BN > 512) throw std::runtime_error("i8gemm_ar: too many slices for TMEM");
@@ -139,7 +165,7 @@ void gemm_ar(const SliceStack& A, int a_row0, int M, const SliceStack& B, double
     P.stack = stack;
     P.nsa = nsa;
     const int ntiles = ((B.R + AR_BN - 1) / AR_BN) * ((M + BM - 1) / BM);
-    P.ar_ntiles = ntiles; P.ar_ksplit = 1; P.ar_kb_per = A.Kp / BK; P.accumulate = 0;
+    P.ar_ntiles = ntiles; P.ar_ksplit = 1; P.ar_kb_per = A.Kp / BK; P.accumulate = 0; P.rowmax = rowmax;
     static const int persist = getenv("B200JK_AR_PERSIST") ? atoi(getenv("B200JK_AR_PERSIST")) : 1;   // 0: one tile per CTA (yardstick)
     dim3 grid(persist ? std::min(ntiles, nsm) : ntiles);
     static const bool dbg = getenv("B200JK_I8_DEBUG") != nullptr;   // cycle stamps of CTA 0 (tuning)

@@ -50,6 +50,9 @@ struct GemmParams {
     // i8gemm_ar_kernel as stage 2 of DF-K (K += Y Y^T / Y G^T): work item = (tile, K range); ar_ksplit K ranges per tile,
     // results meet in fp64 reductions (accumulate), only tiles touching the upper triangle when symmetric
     int ar_ksplit, ar_kb_per, ar_ntiles, accumulate;
+    // stage 1: optional per-output-row maxima (bit pattern of max |C| per row m % inner, 64-bit atomicMax), so that the slicing
+    // of Y needs no row-maximum pass of its own
+    unsigned long long* rowmax;
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -540,6 +543,7 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
             } else if (mlane < P.M) {
                 const int nb = nt * AR_BN;
                 double* dst = P.C + off_lane + nb;
+                double vmax = 0.0;
                 if (((P.N | P.ldc) & 3) == 0 && nb + AR_BN <= P.N) {
                     // every row segment starts on a 32-byte boundary: 256-bit stores, one full sector per lane and instruction
                     // (scalar stores leave 32 eight-byte fragments per instruction for L2 to merge)
@@ -549,12 +553,15 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
                         const double v0 = accv[j] * pow2i(ea_lane + eb.x), v1 = accv[j + 1] * pow2i(ea_lane + eb.y);
                         const double v2 = accv[j + 2] * pow2i(ea_lane + eb.z), v3 = accv[j + 3] * pow2i(ea_lane + eb.w);
                         asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "d"(v0), "d"(v1), "d"(v2), "d"(v3) : "memory");
+                        vmax = fmax(fmax(vmax, fmax(fabs(v0), fabs(v1))), fmax(fabs(v2), fabs(v3)));
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < AR_BN; j++)
-                        if (nb + j < P.N) dst[j] = accv[j] * pow2i(ea_lane + __ldg(P.Eb + nb + j));
+                        if (nb + j < P.N) { const double v = accv[j] * pow2i(ea_lane + __ldg(P.Eb + nb + j)); dst[j] = v; vmax = fmax(vmax, fabs(v)); }
                 }
+                if (P.rowmax && vmax > 0.0)
+                    atomicMax(P.rowmax + (P.inner > 0 ? mlane % P.inner : mlane), (unsigned long long)__double_as_longlong(vmax));
             }
             if (stamp) P.dbg[it * 8 + 6] = clock64();   // tile stored
         }
@@ -679,6 +686,8 @@ constexpr int PT = 64;   // tile edge of split_packed_kernel
 // A_P[ta*64 .., tb*64 ..] from the packed row (coalesced: 64 consecutive doubles per a), writes its slices to the rows
 // (P, a) at columns b and — for off-diagonal tiles — the slices of the transposed tile to the rows (P, b) at columns a,
 // four int8 per 32-bit store.  Columns nao..Kp-1 are written as zeros; pad ROWS of the stack are the caller's (memset).
+// NS7: the slice count is the compile-time 7 (constant shift amounts, digits 3..6 from the low word, 0..1 from the high word)
+template <bool NS7>
 __global__ void __launch_bounds__(256) split_packed_kernel(const double* __restrict__ cderi, long npair, int nao,
                                                            const int* __restrict__ rowexp, int ns, int Rp, int Kp, int out_row0,
                                                            int8_t* __restrict__ out, int* __restrict__ E)
@@ -713,7 +722,36 @@ __global__ void __launch_bounds__(256) split_packed_kernel(const double* __restr
             if (e == EXP_NONE) e = 0;
             if (tcol == 0 && c4 == 0) E[orow0 + r] = e;
             int8_t* dst = out + (orow0 + r) * Kp + tcol * PT + c4;
-            if (ns <= 7) {
+            if constexpr (NS7) {
+                // N = rint(x 2^(48-e)), |N| <= 2^48, as (hi, lo) words of the mantissa of x*scale + 1.5*2^52 (offset 2^51 removed):
+                // digit s sits at bit 7(6-s): s = 3..6 in lo[0,28), s = 2 across the words, s = 1 at hi[3,10), s = 0 = hi >> 10 (signed)
+                const double scN = pow2i(48 - e);
+                unsigned lo[4]; int hi[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const double t_ = fma(pass ? S[c4 + j][rl] : S[rl][c4 + j], scN, 6755399441055744.0);
+                    lo[j] = (unsigned)__double2loint(t_);
+                    hi[j] = (__double2hiint(t_) & 0x000FFFFF) - 0x00080000;     // remove exponent bits and the 2^51 offset
+                }
+                const long sstride = (long)Rp * Kp;
+                unsigned pk[7];
+#pragma unroll
+                for (int s_ = 0; s_ < 7; s_++) pk[s_] = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const unsigned l_ = lo[j];
+                    const int h_ = hi[j];
+                    pk[6] |= (l_ & 127u) << (8 * j);
+                    pk[5] |= ((l_ >> 7) & 127u) << (8 * j);
+                    pk[4] |= ((l_ >> 14) & 127u) << (8 * j);
+                    pk[3] |= ((l_ >> 21) & 127u) << (8 * j);
+                    pk[2] |= (__funnelshift_r(l_, (unsigned)h_, 28) & 127u) << (8 * j);
+                    pk[1] |= (((unsigned)h_ >> 3) & 127u) << (8 * j);
+                    pk[0] |= ((unsigned)(h_ >> 10) & 255u) << (8 * j);
+                }
+#pragma unroll
+                for (int s_ = 0; s_ < 7; s_++) *reinterpret_cast<unsigned*>(dst + s_ * sstride) = pk[s_];
+            } else if (ns <= 7) {
                 // One FP64 operation per element instead of four per digit: N = rint(x 2^(6-e+7(ns-1))) (|N| < 2^48) sits in the
                 // mantissa of x*scale + 1.5*2^52; its digits come out with integer shifts: the top one signed (-64..64), the others
                 // 0..127 (two's-complement style, no carries).  Still an exact representation; the digit products of stage 1 are

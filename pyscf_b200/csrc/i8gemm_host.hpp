@@ -19,7 +19,10 @@ void split_rows_into(SliceStack& S, int row0, const double* X, long ldx, int row
 void packed_rowexp(const double* cderi, long npair, int nao, int nr, int* rowexp, cudaStream_t st);
 void split_packed_into(SliceStack& S, int out_row0, const double* cderi, long npair, int nao, int nr, const int* rowexp, cudaStream_t st);
 void split_packed(SliceStack& S, const double* cderi, long npair, int nao, int nr, const int* rowexp, int ns, cudaStream_t st);
-void gemm_ar(const SliceStack& A, int a_row0, int M, const SliceStack& B, double* C, long ldc, int inner, cudaStream_t st);
+void gemm_ar(const SliceStack& A, int a_row0, int M, const SliceStack& B, double* C, long ldc, int inner, cudaStream_t st,
+             unsigned long long* rowmax = nullptr);
+void split_rows_prepare(SliceStack& S, int rows, int k, int ns, cudaStream_t st);
+void split_rows_premax(SliceStack& S, const double* X, long ldx, int rows, int k, int ns, cudaStream_t st);
 // C[m*ldc + n] += A B^T on the A-stationary all-groups-resident kernel (stage 2 of DF-K); upper triangle only when symmetric
 void gemm_ar_acc(const SliceStack& A, const SliceStack& B, double* C, long ldc, bool symmetric, cudaStream_t st);
 // C[m*ldc + n] (or the transposed scatter when inner>0, see GemmParams) += A B^T
