@@ -17,6 +17,8 @@
  *                            -> nrs8_ji_s2kl / nrs8_li_s2kj      pyscf/lib/vhf/nr_direct_dot.c:1293,1435
  *                            -> CVHFnr_dm_cond, CVHFnrs8_prescreen  optimizer.c:494-518,90-117
  *                            -> lib.hermi_triu                   pyscf/lib/numpy_helper.py:499
+ *   b200jk_incore_set_eri /  _vhf.incore -> CVHFnrs8_incore_drv   pyscf/scf/_vhf.py:283-366, pyscf/lib/vhf/nr_incore.c:624
+ *   b200jk_incore_jk         (J/K from stored integrals, mf._eri; pyscf/scf/hf.py:2499-2508)
  *   b200jk_df_build          incore.cholesky_eri                 pyscf/df/incore.py:129-220
  *                            -> GTOnr3c_drv / GTOint2c           pyscf/lib/gto/fill_nr_3c.c:196, fill_int2c.c:36
  *   b200jk_df_prepare_j /    df_jk.get_j (integral-direct J, no tensor)  pyscf/df/df_jk.py:415-506
@@ -65,6 +67,13 @@ int b200jk_direct_jk(b200jk_handle h, const double* dm, int n_dm, int nao, int h
  * (device pointers); no host<->device copies.  Used by bench.py for the HBM-resident number. */
 int b200jk_direct_jk_device(b200jk_handle h, const double* dm_dev, int n_dm, int nao, int hermi, double* vj_dev,
                             double* vk_dev);
+
+/* In-core path: J/K from two-electron integrals the caller keeps (mf._eri): RHF.get_jk -> dot_eri_dm -> _vhf.incore ->
+ * CVHFnrs8_incore_drv (pyscf/scf/hf.py:2499-2508, 902-961; pyscf/scf/_vhf.py:283-366; pyscf/lib/vhf/nr_incore.c:624).
+ * eri: 8-fold packed [npair(npair+1)/2] (mol.intor('int2e', aosym='s8')), 4-fold [npair, npair] or full [nao]^4, told apart by
+ * its size as dot_eri_dm does; copied to the device once.  dm: [n_dm, nao, nao] of any symmetry; vj / vk may be NULL. */
+int b200jk_incore_set_eri(b200jk_handle h, const double* eri, int64_t neri, int nao);
+int b200jk_incore_jk(b200jk_handle h, const double* dm, int n_dm, int nao, double* vj, double* vk);
 
 /* Density fitting: aux tables are a second libcint-layout set for the auxiliary basis. */
 int b200jk_df_build(b200jk_handle h, const int32_t* aux_atm, int aux_natm, const int32_t* aux_bas, int aux_nbas,

@@ -186,7 +186,7 @@ extern "C" int b200jk_destroy(b200jk_handle h)
     dev_free(h->d_cart_sh); dev_free(h->d_cart_comp); dev_free(h->d_sph_sh); dev_free(h->d_sph_m);
     dev_free(h->d_sh_l); dev_free(h->d_sh_cart); dev_free(h->d_sh_sph); dev_free(h->d_c2s); dev_free(h->d_c2s_off);
     dev_free(h->d_dm_sph); dev_free(h->d_out_sph); dev_free(h->d_dmj); dev_free(h->d_dmk); dev_free(h->d_vj); dev_free(h->d_vk);
-    dev_free(h->d_dmc); dev_free(h->d_counters);
+    dev_free(h->d_dmc); dev_free(h->d_counters); dev_free(h->d_eri);
     if (h->df && h->df_free) h->df_free(h->df);
 #ifndef B200JK_EMULATE
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -479,6 +479,63 @@ extern "C" int b200jk_direct_jk(b200jk_handle h, const double* dm, int n_dm, int
 extern "C" int b200jk_direct_jk_device(b200jk_handle h, const double* dm, int n_dm, int nao, int hermi, double* vj, double* vk)
 {
     return direct_jk_impl(h, dm, n_dm, nao, hermi, vj, vk, true);
+}
+
+// ---- in-core path: J/K from integrals the caller keeps (mf._eri; RHF.get_jk, pyscf/scf/hf.py:2499-2508 -> dot_eri_dm :902-961
+// -> _vhf.incore, pyscf/scf/_vhf.py:283-366 -> CVHFnrs8_incore_drv, pyscf/lib/vhf/nr_incore.c:624) ----
+extern "C" int b200jk_incore_set_eri(b200jk_handle h, const double* eri, int64_t neri, int nao)
+{
+    if (!h) return 1;
+    try {
+        if (!eri || nao < 1) throw std::runtime_error("bad arguments");
+        const long npair = (long)nao * (nao + 1) / 2, n4 = (long)nao * nao * nao * nao;
+        int sym = 0;
+        if (neri == npair * (npair + 1) / 2) sym = 8;
+        else if (neri == npair * npair) sym = 4;
+        else if (neri == n4) sym = 1;
+        if (nao == 1) sym = 1;
+        if (!sym) throw std::runtime_error("eri size matches none of s8 / s4 / s1 for this nao (pyscf/scf/hf.py:934-961)");
+#ifndef B200JK_EMULATE
+        CK(cudaSetDevice(h->device));
+#endif
+        dev_free(h->d_eri);
+        h->d_eri = (double*)dev_alloc((size_t)neri * 8);
+        h2d(h->d_eri, eri, (size_t)neri * 8);
+        dev_sync();
+        h->neri = neri; h->eri_sym = sym;
+    } catch (std::exception& e) { set_err(h, e.what()); return 2; }
+    return 0;
+}
+
+extern "C" int b200jk_incore_jk(b200jk_handle h, const double* dm, int n_dm, int nao, double* vj, double* vk)
+{
+    if (!h) return 1;
+    try {
+        if (!h->d_eri) throw std::runtime_error("call b200jk_incore_set_eri before b200jk_incore_jk");
+        if (!dm || n_dm < 1 || nao < 1) throw std::runtime_error("bad arguments");
+        const long npair = (long)nao * (nao + 1) / 2, n2 = (long)nao * nao;
+        const long expect = h->eri_sym == 8 ? npair * (npair + 1) / 2 : (h->eri_sym == 4 ? npair * npair : n2 * n2);
+        if (expect != h->neri) throw std::runtime_error("nao does not match the stored integrals");
+        if (!vj && !vk) return 0;
+#ifndef B200JK_EMULATE
+        CK(cudaSetDevice(h->device));
+#endif
+        stream_t st = 0;
+        double* d_dm = (double*)dev_alloc((size_t)n_dm * n2 * 8);
+        double* d_j = vj ? (double*)dev_alloc((size_t)n_dm * n2 * 8) : nullptr;
+        double* d_k = vk ? (double*)dev_alloc((size_t)n_dm * n2 * 8) : nullptr;
+        h2d(d_dm, dm, (size_t)n_dm * n2 * 8, st);
+        if (d_j) dev_zero(d_j, (size_t)n_dm * n2 * 8, st);
+        if (d_k) dev_zero(d_k, (size_t)n_dm * n2 * 8, st);
+        IncoreJKFn fn{h->d_eri, h->eri_sym, nao, npair, d_dm, n_dm, d_j, d_k};
+        launch_1d(h->neri, fn, st);
+        if (vj) d2h(vj, d_j, (size_t)n_dm * n2 * 8, st);
+        if (vk) d2h(vk, d_k, (size_t)n_dm * n2 * 8, st);
+        dev_sync();
+        dev_free(d_dm); dev_free(d_j); dev_free(d_k);
+        h->stats.kernel_launches = 1;
+    } catch (std::exception& e) { set_err(h, e.what()); return 2; }
+    return 0;
 }
 
 extern "C" int b200jk_set_profile(b200jk_handle h, int on) { if (!h) return 1; h->profile = on; return 0; }

@@ -180,6 +180,8 @@ struct b200jk_handle_s {
     DFState* df = nullptr;          // density-fitting state (df.cu)
     void (*df_free)(DFState*) = nullptr;
     double class_ms[NPC * NPC] = {0};
+    // in-core path (mf._eri): the stored two-electron integrals, 8-fold / 4-fold packed or full (b200jk_incore_set_eri)
+    double* d_eri = nullptr; long neri = 0; int eri_sym = 0;
 };
 
 
@@ -307,6 +309,56 @@ struct DmCondFn {
                     }
         }
         dmc[idx] = m;
+    }
+};
+
+// In-core J/K from stored integrals (CVHFnrs8_incore_drv, pyscf/lib/vhf/nr_incore.c:624; dot_eri_dm, pyscf/scf/hf.py:902-961):
+// one thread per stored integral, every index permutation it stands for applied with reductions
+//   J_kl += (ij|kl) D_ji ,  K_il += (ij|kl) D_jk        (pyscf/scf/hf.py:906-907)
+// sym 8: eri[pq], p = i(i+1)/2+j >= q = k(k+1)/2+l;  sym 4: eri[p][q];  sym 1: eri[i][j][k][l].
+struct IncoreJKFn {
+    const double* eri; int sym, nao; long npair; const double* dm; int n_dm; double* vj; double* vk;
+    static B2_HD void tri_decode(long t, long& a, long& b)   // t = a(a+1)/2 + b, a >= b
+    {
+        a = (long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while (a * (a + 1) / 2 > t) a--;
+        while ((a + 1) * (a + 2) / 2 <= t) a++;
+        b = t - a * (a + 1) / 2;
+    }
+    B2_HD void one(double v, long i, long j, long k, long l) const
+    {
+        const long n = nao, n2 = n * n;
+        for (int s = 0; s < n_dm; s++) {
+            const double* D = dm + s * n2;
+            if (vj) red_add(vj + s * n2 + k * n + l, v * D[j * n + i]);
+            if (vk) red_add(vk + s * n2 + i * n + l, v * D[j * n + k]);
+        }
+    }
+    B2_HD void operator()(long t) const
+    {
+        if (sym == 1) {
+            const long n = nao;
+            long l = t % n, r = t / n;
+            long k = r % n; r /= n;
+            long j = r % n, i = r / n;
+            one(eri[t], i, j, k, l);
+            return;
+        }
+        long p, q;
+        if (sym == 8) tri_decode(t, p, q);
+        else { p = t / npair; q = t - p * npair; }
+        long i, j, k, l;
+        tri_decode(p, i, j);
+        tri_decode(q, k, l);
+        double v = eri[t];
+        if (v == 0.0) return;
+        if (i == j) v *= 0.5;
+        if (k == l) v *= 0.5;
+        one(v, i, j, k, l); one(v, j, i, k, l); one(v, i, j, l, k); one(v, j, i, l, k);
+        if (sym == 8) {
+            if (p == q) return;      // (ij|kl) with ij == kl: the four bra/ket swaps above are all there is
+            one(v, k, l, i, j); one(v, l, k, i, j); one(v, k, l, j, i); one(v, l, k, j, i);
+        }
     }
 };
 

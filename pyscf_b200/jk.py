@@ -145,6 +145,50 @@ class _OptCache:
 _opt_cache = _OptCache()
 
 
+class IncoreJK:
+    """J/K from stored two-electron integrals (mf._eri): the role of _vhf.incore / dot_eri_dm (pyscf/scf/_vhf.py:283-366,
+    pyscf/scf/hf.py:902-961).  eri: 8-fold packed (mol.intor('int2e', aosym='s8')), 4-fold [npair, npair] or full [nao]^4;
+    copied to the device once."""
+
+    def __init__(self, mol, eri, device=0, libpath=None):
+        env = np.array(mol._env, dtype=np.float64, copy=True)
+        self.handle = _lib.Handle(mol._atm, mol._bas, env, device=device, libpath=libpath)
+        self.nao = int(mol.ao_loc_nr(cart=False)[-1]) if hasattr(mol, 'ao_loc_nr') else mol.nao
+        eri = np.ascontiguousarray(eri, dtype=np.float64)
+        self._eri_id = id(eri)
+        h = self.handle
+        h.check(h.lib.b200jk_incore_set_eri(h._h, _lib.dptr(eri.reshape(-1)), eri.size, self.nao), 'b200jk_incore_set_eri')
+
+    def get_jk(self, dm, hermi=1, with_j=True, with_k=True):
+        dm = np.asarray(dm)
+        if np.iscomplexobj(dm):
+            vjr, vkr = self.get_jk(dm.real, 0, with_j, with_k)
+            vji, vki = self.get_jk(dm.imag, 0, with_j, with_k)
+            return (None if vjr is None else vjr + 1j * vji), (None if vkr is None else vkr + 1j * vki)
+        nao = self.nao
+        if dm.shape[-1] != nao or dm.shape[-2] != nao:
+            raise RuntimeError('dm shape %s does not match nao=%d' % (dm.shape, nao))
+        shape = dm.shape
+        dms = np.ascontiguousarray(dm.reshape(-1, nao, nao), dtype=np.float64)
+        vj = np.empty_like(dms) if with_j else None
+        vk = np.empty_like(dms) if with_k else None
+        h = self.handle
+        h.check(h.lib.b200jk_incore_jk(h._h, _lib.dptr(dms), len(dms), nao, _lib.dptr(vj), _lib.dptr(vk)), 'b200jk_incore_jk')
+        return (None if vj is None else vj.reshape(shape)), (None if vk is None else vk.reshape(shape))
+
+    def close(self):
+        self.handle.close()
+
+
+def incore(mol, eri, dm, hermi=0, with_j=True, with_k=True, device=0, libpath=None):
+    """_vhf.incore(eri, dm, hermi) (pyscf/scf/_vhf.py:283): one-shot J/K from stored integrals."""
+    eng = IncoreJK(mol, eri, device=device, libpath=libpath)
+    try:
+        return eng.get_jk(dm, hermi, with_j, with_k)
+    finally:
+        eng.close()
+
+
 def get_jk(mol, dm, hermi=1, vhfopt=None, with_j=True, with_k=True, omega=None):
     """Drop-in for pyscf.scf.hf.get_jk (pyscf/scf/hf.py:963): returns (vj, vk) shaped like dm."""
     if vhfopt is None:
@@ -159,12 +203,24 @@ def patch(mf, device=0, libpath=None):
     mf._b200_opts here), dropped by mf.reset() (pyscf/scf/hf.py:2331: reset clears _opt) and rebuilt when the molecule's
     integral tables change."""
     cache = _OptCache()
+    incore_eng = {}
 
     def _get_jk(mol=None, dm=None, hermi=1, with_j=True, with_k=True, omega=None):
         if mol is None:
             mol = mf.mol
         if dm is None:
             dm = mf.make_rdm1()
+        # RHF.get_jk (pyscf/scf/hf.py:2499-2508): stored integrals (mf._eri) serve the plain Coulomb operator of the object's
+        # own molecule; everything else goes to the direct path
+        eri = getattr(mf, '_eri', None)
+        if eri is not None and mol is mf.mol and effective_omega(mol, omega) == 0.0:
+            eng = incore_eng.get('eng')
+            if eng is None or incore_eng.get('eri') is not eri:
+                if eng is not None:
+                    eng.close()
+                eng = incore_eng['eng'] = IncoreJK(mol, eri, device=device, libpath=libpath)
+                incore_eng['eri'] = eri
+            return eng.get_jk(dm, hermi, with_j, with_k)
         opt = cache.get(mol, omega, direct_scf_tol=getattr(mf, 'direct_scf_tol', 1e-13), device=device, libpath=libpath)
         return opt.get_jk(dm, hermi, with_j, with_k)
 
@@ -175,6 +231,9 @@ def patch(mf, device=0, libpath=None):
     if cls_reset is not None and not getattr(cls_reset, '_b200_wrapped', False):
         def _reset(mol=None):
             cache.clear()
+            if incore_eng.get('eng') is not None:
+                incore_eng.pop('eng').close()
+                incore_eng.pop('eri', None)
             return cls_reset(mol)
         _reset._b200_wrapped = True
         mf.reset = _reset
