@@ -262,6 +262,12 @@ def measure(args, rank, world, dist):
         hh.check(hh.lib.b200jk_set_shard(hh._h, rank, world), 'b200jk_set_shard')
         hh.lib.b200jk_set_stream(hh._h, ctypes.c_void_p(stream.cuda_stream))
 
+    if not is_df and world > 1:
+        # measured class times of one unsharded build as the cost table of the multi-GPU partition (rank 0's table on every rank)
+        from pyscf_b200.parallel import calibrate_partition
+        h.lib.b200jk_set_stream(h._h, None)
+        calibrate_partition(h, dm_h[None], rank, world)
+        h.lib.b200jk_set_stream(h._h, ctypes.c_void_p(stream.cuda_stream))
     nout = 3 if omega2 else 2
     dm_d = torch.from_numpy(dm_h).to(dev)
     occ_d = torch.from_numpy(occ_h).to(dev)

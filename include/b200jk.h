@@ -129,6 +129,11 @@ int b200jk_get_q_cond(b200jk_handle h, double* q_cond, int nbas);
  * on the DF path — and returns PARTIAL J/K; the caller sums them with one all-reduce (NCCL) per build.
  * The reference analogue is the OpenMP work split + critical-section reduction, pyscf/lib/vhf/nr_direct.c:429-482. */
 int b200jk_set_shard(b200jk_handle h, int rank, int world);
+/* Cost table of the 4-center multi-GPU partition: measured class times ms[100] (entry [cb*10+ck], as b200jk_get_class_times
+ * returns them after an UNSHARDED build with b200jk_set_profile(h, 1)).  With it every class that is small against a rank's
+ * share is given whole to one rank, longest first; without it a fitted model decides and only the cheapest classes go whole.
+ * All ranks must pass the same table (they derive the partition independently); NULL returns to the model. */
+int b200jk_set_class_costs(b200jk_handle h, const double* ms, int n);
 /* Run all work of this handle on the caller's CUDA stream (cudaStream_t cast to void*); NULL restores the
  * handle's own stream.  Lets a host framework (e.g. torch) order and time the calls with its own events. */
 int b200jk_set_stream(b200jk_handle h, void* cuda_stream);

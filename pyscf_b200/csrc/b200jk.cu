@@ -354,7 +354,9 @@ static int direct_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, 
                 int nr = (B.la + B.lb + K.la + K.lb) / 2 + 1;
                 // milliseconds on one B200: least-squares fit to the measured class times of benzene/cc-pVTZ
                 // (profiles/r01_class_times_direct.json, mean abs error 20 %): launch/tail + roots + root sum + digestion
-                jobs.push_back({cb, ck, 0.0976 + 3.14e-9 * pq * nr + 7.6e-10 * pq * nr * ncomp + 2.38e-9 * nq * ncomp + 1.3e-7 * nq});
+                double cost = 0.0976 + 3.14e-9 * pq * nr + 7.6e-10 * pq * nr * ncomp + 2.38e-9 * nq * ncomp + 1.3e-7 * nq;
+                if (h->have_costs && h->class_cost[cb * NPC + ck] > 0.0) cost = h->class_cost[cb * NPC + ck];   // measured on this machine
+                jobs.push_back({cb, ck, cost});
             }
         std::sort(jobs.begin(), jobs.end(), [](const Job& a, const Job& b) { return a.cost > b.cost; });
         // Multi-GPU partition (reference analogue: omp schedule(dynamic) over AO-block triples, pyscf/lib/vhf/nr_direct.c:429-466).
@@ -368,8 +370,12 @@ static int direct_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, 
             for (const Job& jb : jobs) total += jb.cost;
             double cum = 0;
             size_t first_whole = jobs.size();
+            // with MEASURED class times (b200jk_set_class_costs) the balance can be trusted: every class that is small against a
+            // rank's share goes whole; on the fitted model (20 % mean error) only the cheapest 45 % of the work does
+            const double item_cap = h->have_costs ? total / (1.5 * W) : total / (3.0 * W);
+            const double cum_cap = h->have_costs ? total : 0.45 * total;
             for (size_t i = jobs.size(); i-- > 0;) {       // from the cheapest class upwards
-                if (jobs[i].cost > total / (3.0 * W) || cum + jobs[i].cost > 0.45 * total) break;
+                if (jobs[i].cost > item_cap || cum + jobs[i].cost > cum_cap) break;
                 cum += jobs[i].cost;
                 first_whole = i;
             }
@@ -543,6 +549,19 @@ extern "C" int b200jk_get_class_times(b200jk_handle h, double* ms, int n)
 {
     if (!h || !ms || n != NPC * NPC) return 1;
     memcpy(ms, h->class_ms, sizeof(double) * n);
+    return 0;
+}
+
+// Measured per-class times (what b200jk_get_class_times returns after a profiled, unsharded build) as the cost table of the
+// multi-GPU partition.  Every rank must be given the SAME table (the host layer broadcasts rank 0's: pyscf_b200/parallel.py), since
+// the ranks derive the partition independently.  ms == NULL returns to the built-in model.
+extern "C" int b200jk_set_class_costs(b200jk_handle h, const double* ms, int n)
+{
+    if (!h) return 1;
+    if (!ms) { h->have_costs = false; return 0; }
+    if (n != NPC * NPC) { set_err(h, "class cost table must have 100 entries"); return 1; }
+    memcpy(h->class_cost, ms, sizeof(double) * n);
+    h->have_costs = true;
     return 0;
 }
 

@@ -55,6 +55,7 @@ struct DFState {
     // metric factor kept for the integral-direct J (df_jk.get_j): Cholesky L (GPU: column-major lower, emulation: row-major
     // lower) or, when the metric is not positive definite, W = diag(w)^-1/2 V^T [naux, naux_sph] row-major
     double *d_fac = nullptr, *d_W = nullptr;
+    double* d_Linv = nullptr;   // L^-1 row-major (integral-direct J: the metric solve as two streaming passes), made on first use
     bool fac_chol = true;
     // J/K workspaces
     double *d_dmtril = nullptr, *d_rho = nullptr, *d_vjtril = nullptr, *d_A = nullptr, *d_Y = nullptr, *d_occ = nullptr,
@@ -88,7 +89,7 @@ void df_free(DFState* d)
     dev_free(d->d_acart_sh); dev_free(d->d_acart_comp); dev_free(d->d_asph_sh); dev_free(d->d_asph_m);
     dev_free(d->d_ash_l); dev_free(d->d_ash_cart); dev_free(d->d_ash_sph);
     for (int c = 0; c < NPC; c++) dev_free(d->d_ao_off[c]);
-    dev_free(d->d_pairoff); dev_free(d->d_cderi); dev_free(d->d_fac); dev_free(d->d_W);
+    dev_free(d->d_pairoff); dev_free(d->d_cderi); dev_free(d->d_fac); dev_free(d->d_W); dev_free(d->d_Linv);
     dev_free(d->d_dmtril); dev_free(d->d_rho); dev_free(d->d_vjtril); dev_free(d->d_A); dev_free(d->d_Y); dev_free(d->d_occ);
     dev_free(d->d_dm); dev_free(d->d_vk); dev_free(d->d_vj); dev_free(d->d_Y2); dev_free(d->d_occT);
 #ifndef B200JK_EMULATE
@@ -224,7 +225,8 @@ struct UnpackTrilFn {   // vj[s][i][j] from vjtril[s][t]
 // (one row at a time, the L2 -> SM traffic is twice the HBM stream and caps the kernel at ~55 % of the HBM peak).
 constexpr int DFJ_R = 8;
 __global__ void __launch_bounds__(256) dfj_rho_kernel(const double* __restrict__ cderi, const double* __restrict__ dmtril,
-                                                      double* __restrict__ rho, long npair, long r0, long r_end, int naux, long seglen)
+                                                      double* __restrict__ rho, long npair, long r0, long r_end, int naux, long seglen,
+                                                      long dstride)   // distance between the density vectors of two DMs
 {
     const long rb = r0 + (long)blockIdx.y * DFJ_R;
     const int nr = (int)((r_end - rb < DFJ_R) ? r_end - rb : DFJ_R);
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(256) dfj_rho_kernel(const double* __restrict__
     const long t0 = blockIdx.x * seglen;
     const long t1 = (t0 + seglen < npair) ? t0 + seglen : npair;
     const double* row = cderi + rb * npair;
-    const double* d = dmtril + (long)s * npair;
+    const double* d = dmtril + (long)s * dstride;
     double acc[DFJ_R];
 #pragma unroll
     for (int r = 0; r < DFJ_R; r++) acc[r] = 0.0;
@@ -268,7 +270,8 @@ __global__ void __launch_bounds__(256) dfj_rho_kernel(const double* __restrict__
 // vjtril[s][t] += sum_{P in this CTA's row range} rho[s][P] cderi[P][t]  — thread per column, grid (column blocks, row ranges): the
 // row ranges make the launch many waves deep (one row range = 1.2 waves on C60: 30 % of the time in a nearly empty second wave)
 __global__ void __launch_bounds__(256) dfj_acc_kernel(const double* __restrict__ cderi, const double* __restrict__ rho,
-                                                      double* __restrict__ vjtril, long npair, long r0, int nr, int naux, int n_dm)
+                                                      double* __restrict__ vjtril, long npair, long r0, int nr, int naux, int n_dm,
+                                                      long vstride)   // distance between the output vectors of two DMs
 {
     long t = blockIdx.x * 256L + threadIdx.x;
     if (t >= npair) return;
@@ -287,9 +290,28 @@ __global__ void __launch_bounds__(256) dfj_acc_kernel(const double* __restrict__
         }
         for (; r < rb; r++) a0 += rh[r] * __ldcs(col + (long)r * npair);
         const double v = (a0 + a1) + (a2 + a3);
-        if (gridDim.y == 1) vjtril[(long)s * npair + t] += v;
-        else atomicAdd(&vjtril[(long)s * npair + t], v);
+        if (gridDim.y == 1) vjtril[(long)s * vstride + t] += v;
+        else atomicAdd(&vjtril[(long)s * vstride + t], v);
     }
+}
+// y[s][r] += sum_c M[r][c] x[s][c]   and   y[s][c] += sum_r M[r][c] x[s][r]   for a row-major M[nrow][ncol]: the two streaming
+// kernels above, used by the integral-direct J for its contractions with the 3-center batches and with the metric factor
+static void rows_dot(const double* M, long nrow, long ncol, const double* x, long xstride, double* y, int ystride, int n_dm, cudaStream_t st)
+{
+    const long seglen = 16384;
+    const unsigned nseg = (unsigned)((ncol + seglen - 1) / seglen);
+    for (long r0 = 0; r0 < nrow; r0 += 32768L * DFJ_R) {
+        long nr = std::min<long>(32768L * DFJ_R, nrow - r0);
+        dfj_rho_kernel<<<dim3(nseg, (unsigned)((nr + DFJ_R - 1) / DFJ_R), n_dm), 256, 0, st>>>(M, x, y, ncol, r0, r0 + nr, ystride, seglen, xstride);
+    }
+    CK(cudaGetLastError());
+}
+static void cols_acc(const double* M, long nrow, long ncol, const double* x, int xstride, double* y, long ystride, int n_dm, cudaStream_t st)
+{
+    const unsigned ncb = (unsigned)((ncol + 255) / 256);
+    unsigned gy = (unsigned)std::max<long>(1, std::min<long>(nrow / 64, (6L * 148 * 8 + ncb - 1) / ncb));
+    dfj_acc_kernel<<<dim3(ncb, gy), 256, 0, st>>>(M, x, y, ncol, 0, (int)nrow, xstride, n_dm, ystride);
+    CK(cudaGetLastError());
 }
 #endif
 
@@ -702,9 +724,7 @@ extern "C" int b200jk_df_direct_j(b200jk_handle h, const double* dm, int n_dm, i
         // ---- pass 1: rho[s][P] = sum_col (P|col) Dc[s][col]
         for_each_j3c_batch(h, d, d->omega, st, [&](int64_t col0, int64_t cols, const double* d_xa, int, int, int) {
 #ifndef B200JK_EMULATE
-            const double one = 1.0;
-            CKB(cublasDgemm(d->cublas, CUBLAS_OP_T, CUBLAS_OP_N, nas, n_dm, (int)cols, &one, d_xa, (int)cols, d_dc + col0, (int)d->rowlen,
-                            &one, d_rho, nas));
+            rows_dot(d_xa, nas, cols, d_dc + col0, d->rowlen, d_rho, nas, n_dm, st);
 #else
             for (int s = 0; s < n_dm; s++)
                 for (int P = 0; P < nas; P++) {
@@ -716,20 +736,33 @@ extern "C" int b200jk_df_direct_j(b200jk_handle h, const double* dm, int n_dm, i
         });
         // ---- solve the metric equation  (cho_solve / the eigen-decomposed inverse)
 #ifndef B200JK_EMULATE
-        if (d->fac_chol) {
-            int* d_info = (int*)dev_alloc(4);
-            CKS(cusolverDnDpotrs(d->cusolver, CUBLAS_FILL_MODE_LOWER, nas, n_dm, d->d_fac, nas, d_rho, nas, d_info));
-            int info = 0;
-            d2h(&info, d_info, 4, st);
-            CK(cudaStreamSynchronize(st));
-            dev_free(d_info);
-            if (info != 0) throw std::runtime_error("potrs failed");
-        } else {
-            const int nk = d->naux;
+        {
+            // rho <- F^T (F rho) with the row-major factor F = L^-1 (Cholesky; made once per tensor with a triangular solve
+            // against the identity, setup like the factorisation itself) or F = diag(w)^-1/2 V^T (eigen-decomposed metric):
+            // two streaming passes of the hand-written kernels, no library call per J build
+            const double* F = d->d_W;
+            int nk = d->naux;
+            if (d->fac_chol) {
+                if (!d->d_Linv) {
+                    double* X = (double*)dev_alloc((size_t)nas * nas * 8);
+                    dev_zero(X, (size_t)nas * nas * 8, st);
+                    IdentityFn idf{X, nas};
+                    launch_1d(nas, idf, st);
+                    const double one = 1.0;
+                    CKB(cublasDtrsm(d->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, nas, nas, &one, d->d_fac, nas, X, nas));
+                    d->d_Linv = (double*)dev_alloc((size_t)nas * nas * 8);
+                    TransposeFn tr{X, d->d_Linv, nas, nas};      // column-major X = row-major X^T: Linv[i][j] = X(i,j)
+                    launch_1d((long)nas * nas, tr, st);
+                    CK(cudaStreamSynchronize(st));
+                    dev_free(X);
+                }
+                F = d->d_Linv; nk = nas;
+            }
             double* d_tmp = (double*)dev_alloc((size_t)std::max(nk, 1) * n_dm * 8);
-            const double one = 1.0, zero = 0.0;
-            CKB(cublasDgemm(d->cublas, CUBLAS_OP_T, CUBLAS_OP_N, nk, n_dm, nas, &one, d->d_W, nas, d_rho, nas, &zero, d_tmp, nk));
-            CKB(cublasDgemm(d->cublas, CUBLAS_OP_N, CUBLAS_OP_N, nas, n_dm, nk, &one, d->d_W, nas, d_tmp, nk, &zero, d_rho, nas));
+            dev_zero(d_tmp, (size_t)std::max(nk, 1) * n_dm * 8, st);
+            rows_dot(F, nk, nas, d_rho, nas, d_tmp, nk, n_dm, st);
+            dev_zero(d_rho, (size_t)nas * n_dm * 8, st);
+            cols_acc(F, nk, nas, d_tmp, nk, d_rho, nas, n_dm, st);
             CK(cudaStreamSynchronize(st));
             dev_free(d_tmp);
         }
@@ -743,11 +776,12 @@ extern "C" int b200jk_df_direct_j(b200jk_handle h, const double* dm, int n_dm, i
 #endif
         // ---- pass 2: Jc[s][col] = sum_P (P|col) rho[s][P]
         double* d_jc = d_dc;   // reuse
+#ifndef B200JK_EMULATE
+        dev_zero(d_jc, (size_t)d->rowlen * n_dm * 8, st);   // the accumulation kernel adds
+#endif
         for_each_j3c_batch(h, d, d->omega, st, [&](int64_t col0, int64_t cols, const double* d_xa, int, int, int) {
 #ifndef B200JK_EMULATE
-            const double one = 1.0, zero = 0.0;
-            CKB(cublasDgemm(d->cublas, CUBLAS_OP_N, CUBLAS_OP_N, (int)cols, n_dm, nas, &one, d_xa, (int)cols, d_rho, nas, &zero,
-                            d_jc + col0, (int)d->rowlen));
+            cols_acc(d_xa, nas, cols, d_rho, nas, d_jc + col0, d->rowlen, n_dm, st);
 #else
             for (int s = 0; s < n_dm; s++)
                 for (int64_t c = 0; c < cols; c++) {
@@ -935,7 +969,7 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
             mark(B200JK_DF_STAGE_J_RHO);
             for (int r0 = r_lo; r0 < r_hi; r0 += 32768 * DFJ_R) {
                 int nr = std::min(32768 * DFJ_R, r_hi - r0);
-                dfj_rho_kernel<<<dim3(nseg, (nr + DFJ_R - 1) / DFJ_R, n_dm), 256, 0, st>>>(d->d_cderi, d->d_dmtril, d->d_rho, npair, r0, r0 + nr, naux, seglen);
+                dfj_rho_kernel<<<dim3(nseg, (nr + DFJ_R - 1) / DFJ_R, n_dm), 256, 0, st>>>(d->d_cderi, d->d_dmtril, d->d_rho, npair, r0, r0 + nr, naux, seglen, npair);
                 launches++;
             }
             mark(B200JK_DF_STAGE_J_ACC);
@@ -943,7 +977,7 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
                 const unsigned ncb = (unsigned)((npair + 255) / 256);
                 // >= ~6 waves of 148 x 8 CTAs, each row range >= 64 rows
                 unsigned gy = (unsigned)std::max<long>(1, std::min<long>((r_hi - r_lo) / 64, (6L * 148 * 8 + ncb - 1) / ncb));
-                dfj_acc_kernel<<<dim3(ncb, gy), 256, 0, st>>>(d->d_cderi, d->d_rho, d->d_vjtril, npair, r_lo, r_hi - r_lo, naux, n_dm);
+                dfj_acc_kernel<<<dim3(ncb, gy), 256, 0, st>>>(d->d_cderi, d->d_rho, d->d_vjtril, npair, r_lo, r_hi - r_lo, naux, n_dm, npair);
             }
             launches++;
             mark(-1);

@@ -180,6 +180,8 @@ struct b200jk_handle_s {
     DFState* df = nullptr;          // density-fitting state (df.cu)
     void (*df_free)(DFState*) = nullptr;
     double class_ms[NPC * NPC] = {0};
+    double class_cost[NPC * NPC] = {0};   // measured class times handed in by the caller (b200jk_set_class_costs); 0 = use the model
+    bool have_costs = false;
     // in-core path (mf._eri): the stored two-electron integrals, 8-fold / 4-fold packed or full (b200jk_incore_set_eri)
     double* d_eri = nullptr; long neri = 0; int eri_sym = 0;
 };

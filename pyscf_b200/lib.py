@@ -31,7 +31,7 @@ SYMBOLS = ['b200jk_create', 'b200jk_destroy', 'b200jk_set_screening', 'b200jk_di
            'b200jk_last_error', 'b200jk_version', 'b200jk_set_stream', 'b200jk_fp64_peak',
            'b200jk_set_profile', 'b200jk_get_class_times', 'b200jk_df_get_cderi', 'b200jk_i8gemm_test', 'b200jk_df_set_kmode', 'b200jk_set_shard', 'b200jk_df_jk_device', 'b200jk_df_local_rows',
            'b200jk_df_prepare_j', 'b200jk_df_direct_j', 'b200jk_df_stage_times', 'b200jk_df_set_cderi', 'b200jk_df_get_cderi_cols',
-           'b200jk_incore_set_eri', 'b200jk_incore_jk']
+           'b200jk_incore_set_eri', 'b200jk_incore_jk', 'b200jk_set_class_costs']
 
 
 def load(path=None):
@@ -60,6 +60,7 @@ def load(path=None):
     lib.b200jk_df_stage_times.argtypes = [vp, c_double_p, c_int_p, ctypes.c_int]
     lib.b200jk_df_set_cderi.argtypes = [vp, c_double_p, ctypes.c_int, ctypes.c_int]
     lib.b200jk_df_get_cderi.argtypes = [vp, c_double_p, ctypes.c_int, ctypes.c_int]
+    lib.b200jk_set_class_costs.argtypes = [vp, c_double_p, ctypes.c_int]
     lib.b200jk_incore_set_eri.argtypes = [vp, c_double_p, ctypes.c_int64, ctypes.c_int]
     lib.b200jk_incore_jk.argtypes = [vp, c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p]
     lib.b200jk_df_get_cderi_cols.argtypes = [vp, c_double_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]

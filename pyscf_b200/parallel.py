@@ -18,6 +18,42 @@ def _dist():
     return dist
 
 
+def calibrate_partition(handle, dms, rank, world, hermi=1, with_j=True, with_k=True):
+    """Measure the class times of ONE unsharded, profiled 4-center build on this rank's GPU, agree on rank 0's table and hand it
+    to the library as the cost table of the multi-GPU partition (b200jk_set_class_costs): with measured costs every class that
+    is small against a rank's share is given whole to one rank (longest first) instead of being split eight ways.
+    dms: host array [n_dm, nao, nao]; call once per (molecule, screening setup) before the sharded builds."""
+    import torch
+    dist = _dist()
+    h = handle
+    dms = np.ascontiguousarray(dms, dtype=np.float64)
+    n_dm, nao = dms.shape[0], dms.shape[-1]
+    vj = np.empty_like(dms) if with_j else None
+    vk = np.empty_like(dms) if with_k else None
+    h.check(h.lib.b200jk_set_shard(h._h, 0, 1), 'b200jk_set_shard')
+    h.lib.b200jk_set_profile(h._h, 1)
+    try:
+        best = None
+        for _ in range(2):      # the first pass pays cold caches
+            h.check(h.lib.b200jk_direct_jk(h._h, _lib.dptr(dms), n_dm, nao, int(hermi), _lib.dptr(vj), _lib.dptr(vk)), 'b200jk_direct_jk')
+            ms = np.zeros(100)
+            h.check(h.lib.b200jk_get_class_times(h._h, _lib.dptr(ms), 100), 'b200jk_get_class_times')
+            best = ms if best is None else np.minimum(best, ms)
+    finally:
+        h.lib.b200jk_set_profile(h._h, 0)
+        h.check(h.lib.b200jk_set_shard(h._h, rank, world), 'b200jk_set_shard')
+    t = torch.from_numpy(best.copy())
+    if dist.is_initialized() and world > 1:
+        on_gpu = torch.cuda.is_available() and dist.get_backend() == 'nccl'
+        if on_gpu:
+            t = t.to(torch.device('cuda', torch.cuda.current_device()))
+        dist.broadcast(t, src=0)
+        t = t.cpu()
+    table = np.ascontiguousarray(t.numpy(), dtype=np.float64)
+    h.check(h.lib.b200jk_set_class_costs(h._h, _lib.dptr(table), 100), 'b200jk_set_class_costs')
+    return table
+
+
 class ShardedJK:
     """Wraps a jk.VHFOpt (4-center) or df.DF (density fitting) built on THIS rank's GPU."""
 
@@ -34,6 +70,7 @@ class ShardedJK:
         self.h = h
         h.check(h.lib.b200jk_set_shard(h._h, self.rank, self.world), 'b200jk_set_shard')
         self.nao = engine.nao
+        self._calibrated = self.is_df or self.world == 1     # 4-center: class times are measured at the first build
 
     def get_jk(self, dm, hermi=1, with_j=True, with_k=True, device_tensors=None):
         """Partial J/K on this rank, then one all-reduce.  Returns numpy arrays (every rank gets the sum)."""
@@ -53,6 +90,10 @@ class ShardedJK:
             occ = np.ascontiguousarray(np.asarray(dm.mo_coeff).reshape(nao, -1)[:, mask] * np.sqrt(mo_occ[mask]))
             nocc = occ.shape[-1]
         h = self.h
+        if not self._calibrated:
+            if on_gpu:      # the CPU emulation has no class timers: it keeps the model-based partition
+                calibrate_partition(h, dms, self.rank, self.world, hermi, with_j, with_k)
+            self._calibrated = True
         if on_gpu:
             dev = torch.device('cuda', torch.cuda.current_device())
             d_dm = torch.from_numpy(dms).to(dev)
