@@ -54,6 +54,10 @@ typedef struct {
 /* Build a handle from libcint-layout tables (copied).  device: CUDA device ordinal. */
 int b200jk_create(b200jk_handle* out, const int32_t* atm, int natm, const int32_t* bas, int nbas, const double* env,
                   int nenv, int device);
+/* The same with Cartesian AOs when cart != 0 (mol.cart = True; libcint's int2e_cart, pyscf/gto/moleintor.py:772): every dm / vj /
+ * vk then runs over the (l+1)(l+2)/2 Cartesian functions of each shell.  4-center and in-core paths only (DF raises). */
+int b200jk_create2(b200jk_handle* out, const int32_t* atm, int natm, const int32_t* bas, int nbas, const double* env,
+                   int nenv, int device, int cart);
 int b200jk_destroy(b200jk_handle h);
 
 /* Schwarz bounds on device + screened, sorted shell-pair lists.  Must precede b200jk_direct_jk. */

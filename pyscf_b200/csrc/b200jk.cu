@@ -38,11 +38,18 @@ extern "C" const char* b200jk_last_error(b200jk_handle h) { return h ? h->err.c_
 extern "C" int b200jk_create(b200jk_handle* out, const int32_t* atm, int natm, const int32_t* bas, int nbas,
                              const double* env, int nenv, int device)
 {
+    return b200jk_create2(out, atm, natm, bas, nbas, env, nenv, device, 0);
+}
+
+extern "C" int b200jk_create2(b200jk_handle* out, const int32_t* atm, int natm, const int32_t* bas, int nbas,
+                              const double* env, int nenv, int device, int cart)
+{
     if (!out) return 1;
     *out = nullptr;
     b200jk_handle h = new b200jk_handle_s();
     try {
         h->device = device;
+        h->cart = cart ? 1 : 0;
 #ifndef B200JK_EMULATE
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -68,7 +75,8 @@ extern "C" int b200jk_create(b200jk_handle* out, const int32_t* atm, int natm, c
             const double* r = env + atm[b[ATOM_OF] * ATM_SLOTS + PTR_COORD];
             for (int c = 0; c < nc; c++) {
                 DevShell s;
-                s.l = l; s.ref_shell = ib; s.sph_off = sph + c * (2 * l + 1); s.cart_off = 0;
+                const int nf = h->cart ? ncart(l) : 2 * l + 1;
+                s.l = l; s.ref_shell = ib; s.sph_off = sph + c * nf; s.cart_off = 0;
                 s.r[0] = r[0]; s.r[1] = r[1]; s.r[2] = r[2];
                 for (int p = 0; p < np; p++) {
                     double cf = env[b[PTR_COEFF] + c * np + p];
@@ -77,7 +85,7 @@ extern "C" int b200jk_create(b200jk_handle* out, const int32_t* atm, int natm, c
                 s.nprim = (int)s.e.size();
                 tmp.push_back(s);
             }
-            sph += nc * (2 * l + 1);
+            sph += nc * (h->cart ? ncart(l) : 2 * l + 1);
         }
         h->nsph = sph;
         h->nbas_ref = nbas;
@@ -95,14 +103,14 @@ extern "C" int b200jk_create(b200jk_handle* out, const int32_t* atm, int natm, c
             const DevShell& s = h->sh[i];
             sh_l[i] = s.l; sh_cart[i] = s.cart_off; sh_sph[i] = s.sph_off;
             for (int a = 0; a < ncart(s.l); a++) { cart_sh[s.cart_off + a] = i; cart_comp[s.cart_off + a] = a; }
-            for (int m = 0; m < 2 * s.l + 1; m++) { sph_sh[s.sph_off + m] = i; sph_m[s.sph_off + m] = m; }
+            for (int m = 0; m < (h->cart ? ncart(s.l) : 2 * s.l + 1); m++) { sph_sh[s.sph_off + m] = i; sph_m[s.sph_off + m] = m; }
             h->ref_shell_of.push_back(s.ref_shell);
         }
         std::vector<double> c2s;
         std::vector<int> c2s_off;
         for (int l = 0; l <= LMAX; l++) {
             c2s_off.push_back((int)c2s.size());
-            auto T = make_c2s(l);
+            auto T = h->cart ? make_c2c(l) : make_c2s(l);
             c2s.insert(c2s.end(), T.begin(), T.end());
         }
         h->d_cart_sh = upload(cart_sh); h->d_cart_comp = upload(cart_comp);
@@ -216,7 +224,8 @@ extern "C" int b200jk_set_screening(b200jk_handle h, double tol, double omega)
             double* scratch = (double*)dev_alloc((size_t)std::min<long>(chunk, (long)P.all.size()) * ne * ne * 8);
             for (long i0 = 0; i0 < (long)P.all.size(); i0 += chunk) {
                 long n = std::min<long>(chunk, (long)P.all.size() - i0);
-                SchwarzSphFn fn{P.d_all + i0, h->d_prims, h->tb, omega, P.la, P.lb, h->d_c2s + h->c2s_off[P.la], h->d_c2s + h->c2s_off[P.lb], scratch};
+                SchwarzSphFn fn{P.d_all + i0, h->d_prims, h->tb, omega, P.la, P.lb, h->d_c2s + h->c2s_off[P.la], h->d_c2s + h->c2s_off[P.lb], scratch,
+                                h->cart ? ncart(P.la) : 2 * P.la + 1, h->cart ? ncart(P.lb) : 2 * P.lb + 1};
                 launch_1d(n, fn);
                 dev_sync();
             }
@@ -300,7 +309,7 @@ static int direct_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, 
         if (!on_device) { h2d(h->d_dm_sph, dm, ns2 * n_dm * 8, st); dsph = h->d_dm_sph; }
         uint64_t launches = 0;
         // ---- densities in the Cartesian device basis: J sees the symmetric part; K sees sym (and antisym if hermi != 1)
-        Sph2CartFn s2c{dsph, h->d_dmj, h->nsph, h->ncart, 0, h->d_cart_sh, h->d_cart_comp, h->d_sh_l, h->d_sh_sph, h->d_c2s_off, h->d_c2s};
+        Sph2CartFn s2c{dsph, h->d_dmj, h->nsph, h->ncart, 0, h->d_cart_sh, h->d_cart_comp, h->d_sh_l, h->d_sh_sph, h->d_c2s_off, h->d_c2s, h->cart};
         int n_dm_k = n_dm;
         const double* dmk = h->d_dmj;
         bool need_sym = (hermi != 2), need_anti = (hermi != 1);
@@ -322,7 +331,7 @@ static int direct_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, 
             dmk = h->d_dmk;
         }
         // dm_cond on the spherical input, the reference's definition (the Schwarz bounds are spherical too)
-        DmCondSphFn dc{dsph, n_dm, h->d_dmc, h->nsh, h->nsph, h->d_sh_l, h->d_sh_sph};
+        DmCondSphFn dc{dsph, n_dm, h->d_dmc, h->nsh, h->nsph, h->d_sh_l, h->d_sh_sph, h->cart};
         launch_1d((long)h->nsh * h->nsh, dc, st); launches++;
         if (vj) dev_zero(h->d_vj, nc2 * n_dm * 8, st);
         if (vk) dev_zero(h->d_vk, nc2 * n_dm_k * 8, st);

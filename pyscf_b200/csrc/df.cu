@@ -69,7 +69,10 @@ struct DFState {
     cusolverDnHandle_t cusolver = nullptr;
     i8g::SliceStack SA, SC, SY, SG;
     int* d_rowexp = nullptr;   // [nrow][nao] exponents of the rows (P, a) of the unpacked tensor (made once, first tensor-core K call)
-    bool sa_persistent = false; int sa_ns = 0, sa_lo = 0, sa_hi = 0;   // slices of the whole unpacked tensor kept resident (memory permitting)
+    // int8 slices of the unpacked rows [sa_lo, sa_lo + sa_np) of this rank's range kept resident in SA (as many packed rows as
+    // memory permits: all of them when the tensor is small or sharded over enough GPUs); the rest is cut per block into SAt
+    bool sa_decided = false; int sa_np = 0, sa_ns = 0, sa_lo = 0, sa_hi = 0;
+    i8g::SliceStack SAt;
     // per-stage device timers of the last b200jk_df_jk call (CUDA events on the launching stream, read after the final sync)
     std::vector<cudaEvent_t> tm_ev; std::vector<int> tm_tag; size_t tm_used = 0;
 #endif
@@ -93,7 +96,7 @@ void df_free(DFState* d)
     dev_free(d->d_dmtril); dev_free(d->d_rho); dev_free(d->d_vjtril); dev_free(d->d_A); dev_free(d->d_Y); dev_free(d->d_occ);
     dev_free(d->d_dm); dev_free(d->d_vk); dev_free(d->d_vj); dev_free(d->d_Y2); dev_free(d->d_occT);
 #ifndef B200JK_EMULATE
-    d->SA.release(); d->SC.release(); d->SY.release(); d->SG.release();
+    d->SA.release(); d->SAt.release(); d->SC.release(); d->SY.release(); d->SG.release();
     dev_free(d->d_rowexp);
     if (d->cublas) cublasDestroy(d->cublas);
     if (d->cusolver) cusolverDnDestroy(d->cusolver);
@@ -438,6 +441,7 @@ static int df_build_impl(b200jk_handle h, const int32_t* aux_atm, int aux_natm, 
 {
     if (!h) return 1;
     try {
+        if (h->cart) throw std::runtime_error("density fitting with Cartesian AOs (mol.cart = True) is not supported");
         (void)aux_natm; (void)aux_nenv;
         if (h->df) { df_free(h->df); h->df = nullptr; }
         DFState* d = new DFState();
@@ -1005,7 +1009,7 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
             if ((size_t)kb > d->ws_rows || (size_t)ncol > d->ws_nocc || (size_t)n_dm > d->ws_occ_ndm) {
                 dev_free(d->d_A); dev_free(d->d_Y); dev_free(d->d_occ);
                 d->d_A = (double*)dev_alloc((size_t)kb * n2 * 8);
-                d->d_Y = (double*)dev_alloc((size_t)kb * ncol * nao * 8);
+                d->d_Y = (d->k_mode == 1) ? nullptr : (double*)dev_alloc((size_t)kb * ncol * nao * 8);   // FP64 engine only
                 d->d_occ = (double*)dev_alloc((size_t)n_dm * nao * ncol * 8);
                 d->ws_rows = kb; d->ws_nocc = ncol; d->ws_occ_ndm = n_dm;
             }
@@ -1040,30 +1044,40 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
             }
 #endif
 #ifndef B200JK_EMULATE
-            if (tc && !(d->sa_persistent && d->sa_ns == d->k_slices && d->sa_lo == r_lo && d->sa_hi == r_hi)) {
-                // slice the whole unpacked tensor once and keep it (7 B per element) when it fits comfortably
+            if (tc && !(d->sa_decided && d->sa_ns == d->k_slices && d->sa_lo == r_lo && d->sa_hi == r_hi)) {
+                // keep the slices of as many packed rows as fit (7 B per unpacked element): everything when the tensor is small or
+                // sharded over enough GPUs; otherwise a leading part, the rest being re-cut block by block every call
                 size_t freeb = 0, totb = 0;
                 CK(cudaMemGetInfo(&freeb, &totb));
-                size_t rows_tot = (size_t)(r_hi - r_lo) * nao, rp = ((rows_tot + 255) / 256) * 256, kp = ((size_t)nao + 127) / 128 * 128;
-                size_t need = (size_t)d->k_slices * rp * kp;
-                d->sa_persistent = false;
-                if (need < freeb / 2 && rows_tot < (1u << 31)) {
-                    d->SA.alloc((int)rows_tot, nao, d->k_slices);
-                    CK(cudaMemsetAsync(d->SA.q, 0, need, st));
+                freeb += d->SA.cap;                                   // an earlier stack of this handle is reused
+                const size_t kp = ((size_t)nao + 127) / 128 * 128;
+                const size_t per_row = (size_t)d->k_slices * nao * kp;    // bytes of slices per packed row
+                const size_t reserve = (size_t)(kb + 1) * per_row + (12UL << 30);   // the per-block stack + workspaces allocated later
+                const long nloc = r_hi - r_lo;
+                long np = 0;
+                if (freeb * 0.85 > (double)reserve) np = (long)((freeb * 0.85 - (double)reserve) / (double)per_row);
+                if (np >= nloc) np = nloc;
+                else if (np < nloc / 10) np = 0;                      // not worth a second code path
+                while (np > 0 && (size_t)np * nao >= (1UL << 31) - 256) np--;   // row index of the stack is an int
+                d->sa_np = (int)np;
+                if (np > 0) {
+                    const size_t rows_p = (size_t)np * nao, rp = ((rows_p + 255) / 256) * 256;
+                    d->SA.alloc((int)rows_p, nao, d->k_slices);
+                    CK(cudaMemsetAsync(d->SA.q, 0, (size_t)d->k_slices * rp * kp, st));
                     CK(cudaMemsetAsync(d->SA.E, 0, rp * 4, st));
-                    i8g::split_packed_into(d->SA, 0, d->d_cderi + (size_t)r_lo * npair, npair, nao, r_hi - r_lo,
-                                           d->d_rowexp + (size_t)r_lo * nao, st);
-                    d->sa_persistent = true; d->sa_ns = d->k_slices; d->sa_lo = r_lo; d->sa_hi = r_hi;
+                    i8g::split_packed_into(d->SA, 0, d->d_cderi + (size_t)r_lo * npair, npair, nao, (int)np, d->d_rowexp + (size_t)r_lo * nao, st);
                 }
+                d->sa_decided = true; d->sa_ns = d->k_slices; d->sa_lo = r_lo; d->sa_hi = r_hi;
             }
 #endif
             for (int r0 = r_lo; r0 < r_hi; r0 += kb) {
                 int nr = std::min(kb, r_hi - r0);
 #ifndef B200JK_EMULATE
+                const bool blk_resident = tc && (r0 - r_lo + nr <= d->sa_np);
                 if (tc) {
-                    if (!d->sa_persistent) {    // slices of this block straight from the packed rows
+                    if (!blk_resident) {    // slices of this block straight from the packed rows
                         mark(B200JK_DF_STAGE_K_SLICE);
-                        i8g::split_packed(d->SA, d->d_cderi + (size_t)r0 * npair, npair, nao, nr, d->d_rowexp + (size_t)r0 * nao, d->k_slices, st);
+                        i8g::split_packed(d->SAt, d->d_cderi + (size_t)r0 * npair, npair, nao, nr, d->d_rowexp + (size_t)r0 * nao, d->k_slices, st);
                         mark(-1);
                         launches++;
                     }
@@ -1110,7 +1124,7 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
                         // stage 1 leaves the row maxima of Y behind (GemmParams::rowmax): the slicing of Y is one pass
                         const bool premax = (long)nr * ncol >= 8192;
                         if (premax) i8g::split_rows_prepare(d->SY, nao, nr * ncol, d->k_slices, st);
-                        i8g::gemm_ar(d->SA, d->sa_persistent ? (r0 - r_lo) * nao : 0, nr * nao, d->SC, d->d_Y2, (long)nr * ncol, nao, st,
+                        i8g::gemm_ar(blk_resident ? d->SA : d->SAt, blk_resident ? (r0 - r_lo) * nao : 0, nr * nao, d->SC, d->d_Y2, (long)nr * ncol, nao, st,
                                      premax ? d->SY.maxbits : nullptr);
                         tick(1);
                         mark(B200JK_DF_STAGE_K_SLICE);
@@ -1251,6 +1265,7 @@ extern "C" int b200jk_df_set_kmode(b200jk_handle h, int mode, int nslices)
 {
     if (!h || !h->df) { set_err(h, "call b200jk_df_build first"); return 1; }
     if (mode < 0 || mode > 1 || nslices < 1 || nslices > 8) { set_err(h, "bad k mode / slice count"); return 1; }
+    if (mode != h->df->k_mode) h->df->ws_rows = 0;     // the FP64 engine has a work buffer of its own: re-size the workspaces
     h->df->k_mode = mode; h->df->k_slices = nslices;
     return 0;
 }

@@ -109,6 +109,16 @@ inline int cart_index(int l, int lx, int ly)
 }
 // Real solid harmonics (orthonormal on the sphere) in terms of Cartesian monomials, libcint order
 // (p: x,y,z ; l>=2: m=-l..l).  Helgaker, Jorgensen, Olsen, "Molecular Electronic-Structure Theory", eq. 6.4.47.
+// Cartesian AOs (mol.cart = True): libcint's Cartesian functions are the bare monomials times the radial part, with the
+// s and p angular factors it also puts into the spherical functions (pyscf/gto/mole.py:159-181): T = fac(l) * identity
+inline std::vector<double> make_c2c(int l)
+{
+    int nc = ncart(l);
+    std::vector<double> T((size_t)nc * nc, 0.0);
+    const double f = l == 0 ? 0.282094791773878143 : (l == 1 ? 0.488602511902919921 : 1.0);
+    for (int i = 0; i < nc; i++) T[(size_t)i * nc + i] = f;
+    return T;
+}
 inline std::vector<double> make_c2s(int l)
 {
     int nc = ncart(l), ns = 2 * l + 1;
@@ -146,6 +156,7 @@ struct b200jk_handle_s {
     std::string err;
     std::vector<DevShell> sh;
     int nsh = 0, ncart = 0, nsph = 0, nbas_ref = 0;
+    int cart = 0;        // 1: Cartesian AOs (mol.cart = True): "spherical" index space = the ncart(l) libcint Cartesian functions of each shell
     std::vector<PrimPair> prims;
     PrimPair* d_prims = nullptr;
     PairClass pc[NPC];
@@ -197,18 +208,18 @@ struct SchwarzFn {
 };
 // the reference's Schwarz bound (normalised real-spherical functions); scratch: (ncart(la) ncart(lb))^2 doubles per pair
 struct SchwarzSphFn {
-    ShellPair* pairs; const PrimPair* prims; RysTables tb; double omega; int la, lb; const double *Ta, *Tb; double* scratch;
+    ShellPair* pairs; const PrimPair* prims; RysTables tb; double omega; int la, lb; const double *Ta, *Tb; double* scratch; int nfa, nfb;
     B2_HD void operator()(long i) const
     {
         const long ne = (long)((la + 1) * (la + 2) / 2) * ((lb + 1) * (lb + 2) / 2);
-        pairs[i].q = schwarz_pair_sph(la, lb, pairs[i], prims, tb, omega, Ta, Tb, scratch + i * ne * ne);
+        pairs[i].q = schwarz_pair_sph(la, lb, pairs[i], prims, tb, omega, Ta, Tb, scratch + i * ne * ne, nfa, nfb);
     }
 };
 
 // D_cart[s][mu][nu] = sum_{m,m'} T[m,mu] Dsym[m,m'] T[m',nu]; mode 0: (D+D^T)/2, 1: (D-D^T)/2, 2: D as is
 struct Sph2CartFn {
     const double* dsph; double* dcart; int nsph, ncart, mode;
-    const int *cart_sh, *cart_comp, *sh_l, *sh_sph, *c2s_off; const double* c2s;
+    const int *cart_sh, *cart_comp, *sh_l, *sh_sph, *c2s_off; const double* c2s; int cart = 0;
     B2_HD void operator()(long idx) const
     {
         long n2 = (long)ncart * ncart;
@@ -223,10 +234,11 @@ struct Sph2CartFn {
         const double* D = dsph + (size_t)s * nsph * nsph;
         int oa = sh_sph[sa], ob = sh_sph[sb];
         double acc = 0.0;
-        for (int m = 0; m < 2 * la + 1; m++) {
+        const int nfa = cart ? nca : 2 * la + 1, nfb = cart ? ncb : 2 * lb + 1;   // functions per shell in the caller's AO basis
+        for (int m = 0; m < nfa; m++) {
             double ta = Ta[m * nca];
             if (ta == 0.0) continue;
-            for (int mp = 0; mp < 2 * lb + 1; mp++) {
+            for (int mp = 0; mp < nfb; mp++) {
                 double tb_ = Tb[mp * ncb];
                 if (tb_ == 0.0) continue;
                 double d1 = D[(size_t)(oa + m) * nsph + ob + mp], d2 = D[(size_t)(ob + mp) * nsph + oa + m];
@@ -273,11 +285,11 @@ struct Cart2SphFn {
 // dm_cond as the reference defines it (CVHFnr_dm_cond, pyscf/lib/vhf/optimizer.c:494-518): (|D_mn| + |D_nm|)/2 maximised over the
 // SPHERICAL block of the two (device) shells and over all density matrices — the scale the spherical Schwarz bounds live on
 struct DmCondSphFn {
-    const double* dsph; int nd; double* dmc; int nsh, nsph; const int *sh_l, *sh_sph;
+    const double* dsph; int nd; double* dmc; int nsh, nsph; const int *sh_l, *sh_sph; int cart = 0;
     B2_HD void operator()(long idx) const
     {
         int i = (int)(idx / nsh), j = (int)(idx - (long)i * nsh);
-        int ni = 2 * sh_l[i] + 1, nj = 2 * sh_l[j] + 1;
+        int ni = cart ? (sh_l[i] + 1) * (sh_l[i] + 2) / 2 : 2 * sh_l[i] + 1, nj = cart ? (sh_l[j] + 1) * (sh_l[j] + 2) / 2 : 2 * sh_l[j] + 1;
         double m = 0.0;
         for (int s = 0; s < nd; s++) {
             const double* D = dsph + (size_t)s * nsph * nsph;

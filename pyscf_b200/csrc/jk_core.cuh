@@ -638,7 +638,7 @@ B2_HD double schwarz_pair(int la, int lb, const ShellPair& sp, const PrimPair* p
 // u = T_a[A,:] (x) T_b[B,:] (T = the cart->sph matrices the density / J,K transforms use).  Setup only: one thread per shell pair,
 // M in thread-local memory (100 x 100 doubles for an (ff| pair).
 B2_HD double schwarz_pair_sph(int la, int lb, const ShellPair& sp, const PrimPair* prims, const RysTables& tb, double omega,
-                              const double* Ta, const double* Tb, double* M)
+                              const double* Ta, const double* Tb, double* M, int nfa, int nfb)   // nfa, nfb: rows of Ta, Tb
 {
     const int L = la + lb, nr = L + 1;
     const int na = ncart(la), nb = ncart(lb), ne = na * nb;
@@ -715,8 +715,8 @@ B2_HD double schwarz_pair_sph(int la, int lb, const ShellPair& sp, const PrimPai
             }
         }
     double best = 0.0;
-    for (int A = 0; A < 2 * la + 1; A++)
-        for (int B = 0; B < 2 * lb + 1; B++) {
+    for (int A = 0; A < nfa; A++)
+        for (int B = 0; B < nfb; B++) {
             double val = 0.0;
             for (int b = 0; b < nb; b++)
                 for (int a = 0; a < na; a++) {

@@ -36,6 +36,7 @@ def mol_fingerprint(mol):
     hsh.update(np.ascontiguousarray(mol._atm, dtype=np.int32).tobytes())
     hsh.update(np.ascontiguousarray(mol._bas, dtype=np.int32).tobytes())
     hsh.update(env.tobytes())
+    hsh.update(b'cart' if getattr(mol, 'cart', False) else b'sph')
     return hsh.hexdigest()
 
 
@@ -47,11 +48,10 @@ class VHFOpt:
         self.direct_scf_tol = direct_scf_tol
         self.omega = effective_omega(mol, omega)
         self.fingerprint = mol_fingerprint(mol)
-        if getattr(mol, 'cart', False):
-            raise NotImplementedError('cart=True molecules are not supported')
+        self.cart = bool(getattr(mol, 'cart', False))       # Cartesian AOs: libcint's int2e_cart functions (pyscf/gto/mole.py cart=True)
         env = np.array(mol._env, dtype=np.float64, copy=True)
-        self.handle = _lib.Handle(mol._atm, mol._bas, env, device=device, libpath=libpath)
-        self.nao = int(mol.ao_loc_nr(cart=False)[-1]) if hasattr(mol, 'ao_loc_nr') else mol.nao
+        self.handle = _lib.Handle(mol._atm, mol._bas, env, device=device, libpath=libpath, cart=self.cart)
+        self.nao = int(mol.ao_loc_nr(cart=self.cart)[-1]) if hasattr(mol, 'ao_loc_nr') else mol.nao
         h = self.handle
         h.check(h.lib.b200jk_set_screening(h._h, direct_scf_tol, self.omega), 'b200jk_set_screening')
 
@@ -152,8 +152,9 @@ class IncoreJK:
 
     def __init__(self, mol, eri, device=0, libpath=None):
         env = np.array(mol._env, dtype=np.float64, copy=True)
-        self.handle = _lib.Handle(mol._atm, mol._bas, env, device=device, libpath=libpath)
-        self.nao = int(mol.ao_loc_nr(cart=False)[-1]) if hasattr(mol, 'ao_loc_nr') else mol.nao
+        cart = bool(getattr(mol, 'cart', False))
+        self.handle = _lib.Handle(mol._atm, mol._bas, env, device=device, libpath=libpath, cart=cart)
+        self.nao = int(mol.ao_loc_nr(cart=cart)[-1]) if hasattr(mol, 'ao_loc_nr') else mol.nao
         eri = np.ascontiguousarray(eri, dtype=np.float64)
         self._eri_id = id(eri)
         h = self.handle

@@ -26,7 +26,7 @@ class Stats(ctypes.Structure):
 
 _libs = {}
 
-SYMBOLS = ['b200jk_create', 'b200jk_destroy', 'b200jk_set_screening', 'b200jk_direct_jk', 'b200jk_direct_jk_device',
+SYMBOLS = ['b200jk_create', 'b200jk_create2', 'b200jk_destroy', 'b200jk_set_screening', 'b200jk_direct_jk', 'b200jk_direct_jk_device',
            'b200jk_df_build', 'b200jk_df_jk', 'b200jk_df_naux', 'b200jk_get_q_cond', 'b200jk_get_stats',
            'b200jk_last_error', 'b200jk_version', 'b200jk_set_stream', 'b200jk_fp64_peak',
            'b200jk_set_profile', 'b200jk_get_class_times', 'b200jk_df_get_cderi', 'b200jk_i8gemm_test', 'b200jk_df_set_kmode', 'b200jk_set_shard', 'b200jk_df_jk_device', 'b200jk_df_local_rows',
@@ -45,6 +45,8 @@ def load(path=None):
     vp = ctypes.c_void_p
     lib.b200jk_create.argtypes = [ctypes.POINTER(vp), c_int_p, ctypes.c_int, c_int_p, ctypes.c_int, c_double_p,
                                   ctypes.c_int, ctypes.c_int]
+    lib.b200jk_create2.argtypes = [ctypes.POINTER(vp), c_int_p, ctypes.c_int, c_int_p, ctypes.c_int, c_double_p,
+                                   ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.b200jk_destroy.argtypes = [vp]
     lib.b200jk_set_screening.argtypes = [vp, ctypes.c_double, ctypes.c_double]
     lib.b200jk_direct_jk.argtypes = [vp, c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p]
@@ -94,14 +96,15 @@ def iptr(a):
 class Handle:
     """Owns one b200jk_handle (device memory for one molecule/basis)."""
 
-    def __init__(self, atm, bas, env, device=0, libpath=None):
+    def __init__(self, atm, bas, env, device=0, libpath=None, cart=False):
         self.lib = load(libpath)
+        self.cart = bool(cart)
         self._h = ctypes.c_void_p()
         self.atm = np.ascontiguousarray(atm, dtype=np.int32)
         self.bas = np.ascontiguousarray(bas, dtype=np.int32)
         self.env = np.ascontiguousarray(env, dtype=np.float64)
-        rc = self.lib.b200jk_create(ctypes.byref(self._h), iptr(self.atm), len(self.atm), iptr(self.bas),
-                                    len(self.bas), dptr(self.env), len(self.env), device)
+        rc = self.lib.b200jk_create2(ctypes.byref(self._h), iptr(self.atm), len(self.atm), iptr(self.bas),
+                                     len(self.bas), dptr(self.env), len(self.env), device, int(self.cart))
         if rc != 0:
             msg = self.lib.b200jk_last_error(self._h).decode() if self._h else 'b200jk_create failed'
             if self._h:
