@@ -214,7 +214,7 @@ def patch(mf, device=0, libpath=None):
         # RHF.get_jk (pyscf/scf/hf.py:2499-2508): stored integrals (mf._eri) serve the plain Coulomb operator of the object's
         # own molecule; everything else goes to the direct path
         eri = getattr(mf, '_eri', None)
-        if eri is not None and mol is mf.mol and effective_omega(mol, omega) == 0.0:
+        if isinstance(eri, np.ndarray) and mol is mf.mol and effective_omega(mol, omega) == 0.0:
             eng = incore_eng.get('eng')
             if eng is None or incore_eng.get('eri') is not eri:
                 if eng is not None:
