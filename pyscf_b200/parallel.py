@@ -97,9 +97,11 @@ class ShardedJK:
         if on_gpu:
             dev = torch.device('cuda', torch.cuda.current_device())
             d_dm = torch.from_numpy(dms).to(dev)
-            out = torch.zeros((2, n_dm, nao, nao), dtype=torch.float64, device=dev)
+            # only what was asked for is allocated, reduced and copied back (get_k(omega) of a range-separated hybrid asks for K alone)
+            nout = int(bool(with_j)) + int(bool(with_k))
+            out = torch.zeros((nout, n_dm, nao, nao), dtype=torch.float64, device=dev)
             pj = ctypes.c_void_p(out[0].data_ptr()) if with_j else None
-            pk = ctypes.c_void_p(out[1].data_ptr()) if with_k else None
+            pk = ctypes.c_void_p(out[nout - 1].data_ptr()) if with_k else None
             h.lib.b200jk_set_stream(h._h, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
             if self.is_df:
                 d_occ = torch.from_numpy(occ).to(dev) if occ is not None else None
@@ -110,8 +112,13 @@ class ShardedJK:
             else:
                 rc = h.lib.b200jk_direct_jk_device(h._h, ctypes.c_void_p(d_dm.data_ptr()), n_dm, nao, int(hermi), pj, pk)
                 h.check(rc, 'b200jk_direct_jk_device')
-            dist.all_reduce(out)          # the single collective of the build: 2 * n_dm * nao^2 doubles
-            res = out.cpu().numpy()
+            dist.all_reduce(out)          # the single collective of the build: (J, K requested) * n_dm * nao^2 doubles
+            pin = getattr(self, '_pin_out', None)       # device -> pinned host staging (pageable D2H runs at a fraction of the link)
+            if pin is None or pin.shape != out.shape:
+                pin = self._pin_out = torch.empty(out.shape, dtype=torch.float64).pin_memory()
+            pin.copy_(out, non_blocking=False)
+            host = pin.numpy().copy()
+            res = [host[0] if with_j else None, host[nout - 1] if with_k else None]
         else:
             vj = np.zeros_like(dms) if with_j else None
             vk = np.zeros_like(dms) if with_k else None
