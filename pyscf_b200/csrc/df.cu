@@ -69,6 +69,8 @@ struct DFState {
     cusolverDnHandle_t cusolver = nullptr;
     i8g::SliceStack SA, SC, SY, SG;
     int* d_rowexp = nullptr;   // [nrow][nao] exponents of the rows (P, a) of the unpacked tensor (made once, first tensor-core K call)
+    float* d_rownorm2 = nullptr;   // [nrow][nao] squared 2-norms of the same rows (exponent bound of Y, fused Y slicing)
+    double* d_cmax2 = nullptr;     // device scalar: max squared column norm of the right factor of stage 1
     // int8 slices of the unpacked rows [sa_lo, sa_lo + sa_np) of this rank's range kept resident in SA (as many packed rows as
     // memory permits: all of them when the tensor is small or sharded over enough GPUs); the rest is cut per block into SAt
     bool sa_decided = false; int sa_np = 0, sa_ns = 0, sa_lo = 0, sa_hi = 0;
@@ -97,7 +99,7 @@ void df_free(DFState* d)
     dev_free(d->d_dm); dev_free(d->d_vk); dev_free(d->d_vj); dev_free(d->d_Y2); dev_free(d->d_occT);
 #ifndef B200JK_EMULATE
     d->SA.release(); d->SAt.release(); d->SC.release(); d->SY.release(); d->SG.release();
-    dev_free(d->d_rowexp);
+    dev_free(d->d_rowexp); dev_free(d->d_rownorm2); dev_free(d->d_cmax2);
     if (d->cublas) cublasDestroy(d->cublas);
     if (d->cusolver) cusolverDnDestroy(d->cusolver);
 #endif
@@ -186,12 +188,13 @@ struct UnpackFn {
     }
 };
 
-struct UnpackLongFn {   // G[l][P * nao + k] = A_P[l][k] from the packed rows r0 + P: the unpacked block as nao long rows
-    const double* tril; double* out; int nao; long npair; int r0; long ld;
+struct UnpackLongFn {   // G[l][P * ncolp + k] = A_P[l][k] (0 for the pad columns k >= nao) from the packed rows r0 + P: the block as nao long rows
+    const double* tril; double* out; int nao; long npair; int r0; long ld; int ncolp;
     B2_HD void operator()(long idx) const
     {
         long l = idx / ld, e = idx - l * ld;
-        long P = e / nao, k = e - P * nao;
+        long P = e / ncolp, k = e - P * ncolp;
+        if (k >= nao) { out[idx] = 0.0; return; }
         long hi = l >= k ? l : k, lo = l >= k ? k : l;
         out[idx] = tril[(r0 + P) * npair + hi * (hi + 1) / 2 + lo];
     }
@@ -1008,7 +1011,7 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
             int ncol = use_occ ? nocc : nao;
             if ((size_t)kb > d->ws_rows || (size_t)ncol > d->ws_nocc || (size_t)n_dm > d->ws_occ_ndm) {
                 dev_free(d->d_A); dev_free(d->d_Y); dev_free(d->d_occ);
-                d->d_A = (double*)dev_alloc((size_t)kb * n2 * 8);
+                d->d_A = (double*)dev_alloc((size_t)kb * nao * ((nao + 15) & ~15) * 8);   // rows of nao columns padded to 16 (general-density G operand)
                 d->d_Y = (d->k_mode == 1) ? nullptr : (double*)dev_alloc((size_t)kb * ncol * nao * 8);   // FP64 engine only
                 d->d_occ = (double*)dev_alloc((size_t)n_dm * nao * ncol * 8);
                 d->ws_rows = kb; d->ws_nocc = ncol; d->ws_occ_ndm = n_dm;
@@ -1032,14 +1035,16 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
             if (tc) {
                 // int32 accumulation bound: pairs(<=ns) * K * 64*64 < 2^31
                 int kmax = (int)((1L << 19) / d->k_slices);
-                kb = std::max(1, std::min(kb, kmax / ncol));
+                kb = std::max(1, std::min(kb, kmax / ((ncol + 15) & ~15)));   // stage 2 contracts over (P, i) with i padded to 16
                 // stage 1 contracts over nao with tensor digits up to 127 (split_packed_kernel) against balanced digits (<= 64)
                 if ((long)nao * d->k_slices * 127 * 64 >= (1L << 31)) throw std::runtime_error("nao too large for the int32 accumulators of DF-K stage 1");
                 if ((size_t)kb * ncol * nao > d->y2_cap) { dev_free(d->d_Y2); d->y2_cap = (size_t)kb * ncol * nao; d->d_Y2 = (double*)dev_alloc(d->y2_cap * 8); }
                 if ((size_t)ncol * nao > d->occT_cap) { dev_free(d->d_occT); d->occT_cap = (size_t)ncol * nao; d->d_occT = (double*)dev_alloc(d->occT_cap * 8); }
                 if (!d->d_rowexp) {
                     d->d_rowexp = (int*)dev_alloc((size_t)std::max(d->nrow, 1) * nao * 4);
-                    i8g::packed_rowexp(d->d_cderi, npair, nao, d->nrow, d->d_rowexp, st);
+                    d->d_rownorm2 = (float*)dev_alloc((size_t)std::max(d->nrow, 1) * nao * 4);
+                    d->d_cmax2 = (double*)dev_alloc(8);
+                    i8g::packed_rowexp(d->d_cderi, npair, nao, d->nrow, d->d_rowexp, d->d_rownorm2, st);
                 }
             }
 #endif
@@ -1083,9 +1088,12 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
                     }
                     if (!use_occ) {             // general density: the block once more as nao long rows G[l][(P,k)] = A_P[l][k]
                         mark(B200JK_DF_STAGE_K_SLICE);
-                        UnpackLongFn ul{d->d_cderi, d->d_A, nao, npair, r0, (long)nr * nao};
-                        launch_1d((long)nr * n2, ul, st);
-                        i8g::split_rows(d->SG, d->d_A, (long)nr * nao, nao, nr * nao, d->k_slices, st);
+                        // same (P, k) column layout as Y: k padded to 16 when stage 1 cuts the slices of Y itself
+                        static const bool fuse_y_g = getenv("B200JK_NO_YFUSE") == nullptr;
+                        const int gcol = fuse_y_g ? ((nao + 15) & ~15) : nao;
+                        UnpackLongFn ul{d->d_cderi, d->d_A, nao, npair, r0, (long)nr * gcol, gcol};
+                        launch_1d((long)nao * nr * gcol, ul, st);
+                        i8g::split_rows(d->SG, d->d_A, (long)nr * gcol, nao, nr * gcol, d->k_slices, st);
                         mark(-1);
                         launches += 2;
                     }
@@ -1107,6 +1115,7 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
                             TransposeFn tr{use_occ ? d->d_occ + (size_t)s * nao * nocc : d->d_dm + (size_t)s * n2, d->d_occT, nao, ncol};
                             launch_1d((long)nao * ncol, tr, st);
                             i8g::split_rows(d->SC, d->d_occT, nao, ncol, nao, d->k_slices, st); launches += 2;
+                            i8g::colnorm_max(d->d_occT, nao, ncol, nao, d->d_cmax2, st);
                         }
                         static const bool prof = getenv("B200JK_DF_PROFILE") != nullptr;
                         static double tacc[5];
@@ -1121,6 +1130,17 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
                         tick(-1);
                         tick(0);
                         mark(B200JK_DF_STAGE_K_GEMM1);
+                        static const bool fuse_y = getenv("B200JK_NO_YFUSE") == nullptr;
+                        if (fuse_y) {
+                            // stage 1 cuts the int8 slices of Y itself: the row exponents are bounded BEFORE the GEMM
+                            // (||A_P[nu,:]||_2 max_i ||C~_i||_2), fp64 Y is never written
+                            const int ncolp = (ncol + 15) & ~15;
+                            i8g::y_prepare(d->SY, nao, nr, ncolp, d->k_slices, d->d_rownorm2 + (size_t)r0 * nao, d->d_cmax2, st);
+                            i8g::gemm_ar(blk_resident ? d->SA : d->SAt, blk_resident ? (r0 - r_lo) * nao : 0, nr * nao, d->SC, nullptr, 0, nao, st,
+                                         nullptr, &d->SY, ncolp);
+                            tick(1);
+                            mark(B200JK_DF_STAGE_K_SLICE);
+                        } else {
                         // stage 1 leaves the row maxima of Y behind (GemmParams::rowmax): the slicing of Y is one pass
                         const bool premax = (long)nr * ncol >= 8192;
                         if (premax) i8g::split_rows_prepare(d->SY, nao, nr * ncol, d->k_slices, st);
@@ -1130,6 +1150,7 @@ static int df_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, cons
                         mark(B200JK_DF_STAGE_K_SLICE);
                         if (premax) i8g::split_rows_premax(d->SY, d->d_Y2, (long)nr * ncol, nao, nr * ncol, d->k_slices, st);
                         else i8g::split_rows(d->SY, d->d_Y2, (long)nr * ncol, nao, nr * ncol, d->k_slices, st);
+                        }
                         tick(2);
                         mark(B200JK_DF_STAGE_K_GEMM2);
                         // K += Y Y^T (orbitals) or Y G^T (general density; only its upper triangle when D, hence K, is symmetric)

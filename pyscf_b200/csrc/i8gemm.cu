@@ -35,6 +35,7 @@ static void make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t 
 
 void SliceStack::alloc(int rows, int k, int ns_)
 {
+    if (rows != R || k != K || ns_ != ns) zeroed_for = 0;
     R = rows; K = k; ns = ns_;
     Rp = ((rows + 255) / 256) * 256;   // multiple of both BM and BN
     Kp = ((k + BK - 1) / BK) * BK;
@@ -57,6 +58,7 @@ void split_rows_into(SliceStack& S, int row0, const double* X, long ldx, int row
 void split_rows_prepare(SliceStack& S, int rows, int k, int ns, cudaStream_t st)
 {
     S.alloc(rows, k, ns);
+    S.zeroed_for = 0;
     CK(cudaMemsetAsync(S.maxbits, 0, (size_t)rows * 8, st));
 }
 void split_rows_premax(SliceStack& S, const double* X, long ldx, int rows, int k, int ns, cudaStream_t st)
@@ -76,6 +78,7 @@ void split_rows_premax(SliceStack& S, const double* X, long ldx, int rows, int k
 void split_rows(SliceStack& S, const double* X, long ldx, int rows, int k, int ns, cudaStream_t st)
 {
     S.alloc(rows, k, ns);
+    S.zeroed_for = 0;
     if (S.Rp > rows) {   // zero the pad rows of every slice
         for (int s = 0; s < ns; s++)
             CK(cudaMemsetAsync(S.q + ((size_t)s * S.Rp + rows) * S.Kp, 0, (size_t)(S.Rp - rows) * S.Kp, st));
@@ -95,16 +98,41 @@ void split_rows(SliceStack& S, const double* X, long ldx, int rows, int k, int n
 
 // ---- the DF tensor from its packed rows (see i8gemm.cuh (3)) ----
 // rowexp[nr][nao]: exponent of every row (P, a) of the unpacked tensor; cderi points at the first of the nr packed rows
-void packed_rowexp(const double* cderi, long npair, int nao, int nr, int* rowexp, cudaStream_t st)
+void packed_rowexp(const double* cderi, long npair, int nao, int nr, int* rowexp, float* rownorm2, cudaStream_t st)
 {
     CK(cudaMemsetAsync(rowexp, 0x80, (size_t)nr * nao * 4, st));     // EXP_NONE
+    if (rownorm2) CK(cudaMemsetAsync(rownorm2, 0, (size_t)nr * nao * 4, st));
     static bool configured = false;
     if (!configured) { CK(cudaFuncSetAttribute(packed_rowexp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); configured = true; }
-    if ((size_t)nao * 4 > 160 * 1024) throw std::runtime_error("packed_rowexp: nao too large for the shared-memory exponent table");
+    if ((size_t)nao * 8 > 160 * 1024) throw std::runtime_error("packed_rowexp: nao too large for the shared-memory tables");
     for (int p0 = 0; p0 < nr; p0 += 32768) {
         int n = std::min(32768, nr - p0);
-        packed_rowexp_kernel<<<dim3((nao + 63) / 64, n), 256, (size_t)nao * 4, st>>>(cderi + (size_t)p0 * npair, npair, nao, rowexp + (size_t)p0 * nao);
+        packed_rowexp_kernel<<<dim3((nao + 63) / 64, n), 256, (size_t)nao * 8, st>>>(cderi + (size_t)p0 * npair, npair, nao, rowexp + (size_t)p0 * nao,
+                                                                                      rownorm2 ? rownorm2 + (size_t)p0 * nao : nullptr);
     }
+    CK(cudaGetLastError());
+}
+// ---- stage 1 cutting the slices of Y itself (GemmParams::yq) ----
+// cmax2[0] = max_i ||row i of X||^2 (X = the right factor of stage 1 as rows [ncol][k])
+void colnorm_max(const double* X, long ldx, int nrows, int k, double* cmax2, cudaStream_t st)
+{
+    CK(cudaMemsetAsync(cmax2, 0, 8, st));
+    colnorm_max_kernel<<<(nrows + 7) / 8, 256, 0, st>>>(X, ldx, nrows, k, reinterpret_cast<unsigned long long*>(cmax2));
+    CK(cudaGetLastError());
+}
+// the Y stack of one block: rows = nao, columns (P, i) with i padded to a multiple of 16; pads are zeroed when the shape changes
+// (the epilogue of stage 1 overwrites every real element of every block), exponents = the Cauchy-Schwarz bound of each row
+void y_prepare(SliceStack& S, int nao, int nr, int ncolp, int ns, const float* rownorm2_block, const double* cmax2, cudaStream_t st)
+{
+    const int k = nr * ncolp;
+    S.alloc(nao, k, ns);
+    const bool same = (S.zeroed_for == (long)nao * 1000003L + k);
+    if (!same) {
+        CK(cudaMemsetAsync(S.q, 0, (size_t)ns * S.Rp * S.Kp, st));
+        CK(cudaMemsetAsync(S.E, 0, (size_t)S.Rp * 4, st));
+        S.zeroed_for = (long)nao * 1000003L + k;
+    }
+    yexp_bound_kernel<<<(nao + 255) / 256, 256, 0, st>>>(rownorm2_block, nr, nao, cmax2, S.E);
     CK(cudaGetLastError());
 }
 // slices of the unpacked rows (P, a), P in [0, nr), into the rows out_row0 + P nao + a of an allocated stack
@@ -138,7 +166,7 @@ void split_packed(SliceStack& S, const double* cderi, long npair, int nao, int n
 
 // stage-1 GEMM of DF-K with all slice-pair groups resident in TMEM (i8gemm_ar_kernel): rows [a_row0, a_row0+M) of A
 void gemm_ar(const SliceStack& A, int a_row0, int M, const SliceStack& B, double* C, long ldc, int inner, cudaStream_t st,
-             unsigned long long* rowmax)
+             unsigned long long* rowmax, const SliceStack* Yout, int y_ncolp)
 {
     if (A.Kp != B.Kp || A.ns != B.ns) throw std::runtime_error("i8gemm_ar: operand stacks disagree");
     if (A.ns * AR_BN > 512) throw std::runtime_error("i8gemm_ar: too many slices for TMEM");
@@ -166,6 +194,11 @@ void gemm_ar(const SliceStack& A, int a_row0, int M, const SliceStack& B, double
     P.nsa = nsa;
     const int ntiles = ((B.R + AR_BN - 1) / AR_BN) * ((M + BM - 1) / BM);
     P.ar_ntiles = ntiles; P.ar_ksplit = 1; P.ar_kb_per = A.Kp / BK; P.accumulate = 0; P.rowmax = rowmax;
+    if (Yout) {
+        if (inner <= 0 || (y_ncolp & 15) || y_ncolp < B.R || (long)((M + inner - 1) / inner) * y_ncolp > Yout->Kp || Yout->R != inner)
+            throw std::runtime_error("i8gemm_ar: inconsistent Y stack");
+        P.yq = Yout->q; P.Ey = Yout->E; P.y_Rp = Yout->Rp; P.y_Kp = Yout->Kp; P.y_ncolp = y_ncolp;
+    }
     static const int persist = getenv("B200JK_AR_PERSIST") ? atoi(getenv("B200JK_AR_PERSIST")) : 1;   // 0: one tile per CTA (yardstick)
     dim3 grid(persist ? std::min(ntiles, nsm) : ntiles);
     static const bool dbg = getenv("B200JK_I8_DEBUG") != nullptr;   // cycle stamps of CTA 0 (tuning)

@@ -53,6 +53,10 @@ struct GemmParams {
     // stage 1: optional per-output-row maxima (bit pattern of max |C| per row m % inner, 64-bit atomicMax), so that the slicing
     // of Y needs no row-maximum pass of its own
     unsigned long long* rowmax;
+    // stage 1 writing the int8 slices of Y itself (no fp64 Y): yq = base of the Y stack [ns][y_Rp][y_Kp], row = m % inner,
+    // column = (m / inner) * y_ncolp + n (y_ncolp = N padded to 16), Ey[row] = exponent BOUND of the row (known before the GEMM:
+    // Cauchy-Schwarz on the row norms of the tensor block and the column norms of the right factor)
+    int8_t* yq; const int* Ey; int y_Rp, y_Kp, y_ncolp;
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -528,7 +532,45 @@ i8gemm_ar_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
             // lane = output row (the TMEM lane): its 64 columns are contiguous in C, so every lane streams its own 512 B;
             // the partial sectors of neighbouring stores merge in L2.  No transpose, no shuffles; the column exponents come
             // through the read-only path, so they are not ordered behind the stores of the previous row.
-            if (P.accumulate) {
+            if (P.yq) {
+                // Y never exists in fp64: scale the row by its exponent bound and cut the balanced 7-bit digits here
+                // (round-to-nearest by the 1.5*2^52 trick: two adds per digit instead of a rounding and a conversion instruction)
+                if (mlane < P.M) {
+                    const int nb = nt * AR_BN;
+                    const int yrow = mlane % P.inner;
+                    const long ycol0 = (long)(mlane / P.inner) * P.y_ncolp + nb;
+                    const int esc = ea_lane + 6 - __ldg(P.Ey + yrow);
+                    int8_t* dst0 = P.yq + (long)yrow * P.y_Kp + ycol0;
+                    const long sstride = (long)P.y_Rp * P.y_Kp;
+#pragma unroll
+                    for (int j0 = 0; j0 < AR_BN; j0 += 16) {
+                        if (nb + j0 >= P.y_ncolp) break;
+                        double rr[16];
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const int4 eb = __ldg(reinterpret_cast<const int4*>(P.Eb + nb + j0 + j));
+                            rr[j] = accv[j0 + j] * pow2i(esc + eb.x); rr[j + 1] = accv[j0 + j + 1] * pow2i(esc + eb.y);
+                            rr[j + 2] = accv[j0 + j + 2] * pow2i(esc + eb.z); rr[j + 3] = accv[j0 + j + 3] * pow2i(esc + eb.w);
+                        }
+                        for (int s_ = 0; s_ < ns; s_++) {
+                            unsigned w[4];
+#pragma unroll
+                            for (int q4 = 0; q4 < 4; q4++) {
+                                unsigned pack = 0;
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    const double t_ = rr[4 * q4 + j] + 6755399441055744.0;
+                                    const double qv = t_ - 6755399441055744.0;
+                                    pack |= ((unsigned)__double2loint(t_) & 255u) << (8 * j);
+                                    rr[4 * q4 + j] = (rr[4 * q4 + j] - qv) * 128.0;
+                                }
+                                w[q4] = pack;
+                            }
+                            *reinterpret_cast<uint4*>(dst0 + s_ * sstride + j0) = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                }
+            } else if (P.accumulate) {
                 // partial result of this K range: fp64 reductions; every lane walks its own row, so the 32 reductions of one
                 // instruction go to 32 rows (scattered, but this epilogue runs once per 128 x 64 x K-range item)
                 if (mlane < P.M) {
@@ -653,32 +695,73 @@ __device__ __forceinline__ int frexp_exp(double v)   // e with |v| = f 2^e, f in
 // rowexp[P][a] = exponent of max_b |A_P[a][b]|, accumulated with integer atomicMax; the caller fills rowexp with EXP_NONE.
 // grid (ceil(nao / 64), nr): a CTA reads the packed rows a0 .. a0+63 of auxiliary row P once, coalesced; an element (a, b)
 // counts for row a (warp reduction) and for row b (shared-memory atomicMax, flushed once per CTA).
-__global__ void __launch_bounds__(256) packed_rowexp_kernel(const double* __restrict__ cderi, long npair, int nao, int* __restrict__ rowexp)
+// rownorm2[P][a] (optional, zeroed by the caller) = sum_b A_P[a][b]^2 in single precision: the row norms behind the exponent
+// bound of Y when stage 1 cuts the slices of Y itself.
+__global__ void __launch_bounds__(256) packed_rowexp_kernel(const double* __restrict__ cderi, long npair, int nao, int* __restrict__ rowexp,
+                                                            float* __restrict__ rownorm2)
 {
-    extern __shared__ int emax_s[];          // [nao]
+    extern __shared__ int emax_s[];          // [nao] exponents, then [nao] partial squared norms
+    float* ss = reinterpret_cast<float*>(emax_s + nao);
     const int P = blockIdx.y;
     const double* row = cderi + (long)P * npair;
     const int a0 = blockIdx.x * 64, a1 = (a0 + 64 < nao) ? a0 + 64 : nao;
-    for (int b = threadIdx.x; b < a1; b += 256) emax_s[b] = EXP_NONE;
+    for (int b = threadIdx.x; b < a1; b += 256) { emax_s[b] = EXP_NONE; ss[b] = 0.0f; }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int a = a0 + warp; a < a1; a += 8) {
         const double* x = row + (long)a * (a + 1) / 2;
         int em = EXP_NONE;
+        float sq = 0.0f;
         for (int b = lane; b <= a; b += 32) {
             const double v = fabs(x[b]);
             if (v > 0.0) {
                 const int e = frexp_exp(v);
                 em = e > em ? e : em;
                 if (e > emax_s[b]) atomicMax(&emax_s[b], e);
+                const float v2 = (float)(v * v);
+                sq += v2;
+                if (rownorm2 && b < a) atomicAdd(&ss[b], v2);      // the element also belongs to row b of the symmetric matrix
             }
         }
-        for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, em, o); em = t > em ? t : em; }
-        if (lane == 0 && em != EXP_NONE) atomicMax(&rowexp[(long)P * nao + a], em);
+        for (int o = 16; o > 0; o >>= 1) {
+            const int t = __shfl_xor_sync(0xffffffffu, em, o); em = t > em ? t : em;
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        }
+        if (lane == 0 && em != EXP_NONE) {
+            atomicMax(&rowexp[(long)P * nao + a], em);
+            if (rownorm2) atomicAdd(&rownorm2[(long)P * nao + a], sq);
+        }
     }
     __syncthreads();
     for (int b = threadIdx.x; b < a1; b += 256)
-        if (emax_s[b] != EXP_NONE) atomicMax(&rowexp[(long)P * nao + b], emax_s[b]);
+        if (emax_s[b] != EXP_NONE) {
+            atomicMax(&rowexp[(long)P * nao + b], emax_s[b]);
+            if (rownorm2 && ss[b] > 0.0f) atomicAdd(&rownorm2[(long)P * nao + b], ss[b]);
+        }
+}
+
+// Exponent bound of the rows of Y = A_P C~ over a block of nr auxiliary rows, before the GEMM (Cauchy-Schwarz):
+//   |Y[nu,(P,i)]| <= ||A_P[nu,:]||_2 * max_i ||C~[:,i]||_2      Ey[nu] = exponent of 1.001 * max_P ... (|y| < 2^Ey)
+// cmax2: device scalar, max_i sum_mu C~[mu,i]^2 (colnorm_max_kernel).  One thread per nu.
+__global__ void yexp_bound_kernel(const float* __restrict__ rownorm2, int nr, int nao, const double* __restrict__ cmax2, int* __restrict__ Ey)
+{
+    const int nu = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nu >= nao) return;
+    float m = 0.0f;
+    for (int P = 0; P < nr; P++) m = fmaxf(m, rownorm2[(long)P * nao + nu]);
+    const double bound = 1.001 * sqrt((double)m * 1.0001 * cmax2[0]);
+    Ey[nu] = bound > 0.0 ? frexp_exp(bound) : 0;
+}
+// cmax2[0] = max over the rows i of X[nrows][k] (row stride ldx) of sum_k X[i][k]^2; one warp per row; cmax2 zeroed by the caller
+__global__ void __launch_bounds__(256) colnorm_max_kernel(const double* __restrict__ X, long ldx, int nrows, int k, unsigned long long* __restrict__ cmax2)
+{
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= nrows) return;
+    const double* x = X + (long)r * ldx;
+    double sq = 0.0;
+    for (int c = lane; c < k; c += 32) sq += x[c] * x[c];
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (lane == 0 && sq > 0.0) atomicMax(cmax2, (unsigned long long)__double_as_longlong(sq));
 }
 
 constexpr int PT = 64;   // tile edge of split_packed_kernel

@@ -1,5 +1,4 @@
 cd "${GRAFT_REPO_ROOT}"; mkdir -p gpurun_out
-echo "== all gpu tests"; timeout 1400 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | cut -c1-160
-echo "== bench (default, as the driver runs it)"; timeout 1200 python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/r02p_bench_n1.json 2> gpurun_out/r02p_bench_n1.err; tail -c 400 gpurun_out/r02p_bench_n1.err; python tools/bench_brief.py gpurun_out/r02p_bench_n1.json | cut -c1-260
-echo "== reference arm"; timeout 600 python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 > gpurun_out/r02p_ref.json 2> gpurun_out/r02p_ref.err; python tools/bench_brief.py gpurun_out/r02p_ref.json | cut -c1-400
+echo "== df tests"; timeout 1400 python -m pytest tests -m gpu -x -q -k "test_df or i8gemm" 2>&1 | tail -12
+echo "== c60"; timeout 600 python bench.py --workload c60-def2svp-df --steps 5 --warmup 3 --no-cpu > gpurun_out/r02q_c60.json 2> gpurun_out/r02q_c60.err; tail -c 300 gpurun_out/r02q_c60.err; python tools/bench_brief.py gpurun_out/r02q_c60.json | cut -c1-900
+echo "== taxol"; timeout 600 python bench.py --workload taxol-def2tzvp-df --steps 4 --warmup 3 --no-cpu > gpurun_out/r02q_taxol.json 2> gpurun_out/r02q_taxol.err; python tools/bench_brief.py gpurun_out/r02q_taxol.json | cut -c1-900
