@@ -147,6 +147,23 @@ def algorithmic_bytes(opt):
     return 3 * n * n * 8 + st['n_pairs'] * 48
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed `ncu --set full` summary of the
+    C60 bench command (profiles/r02_ncu_summary.txt); None when the profile is not there."""
+    try:
+        tot, on = 0.0, False
+        for line in open(os.path.join(ROOT, 'profiles', 'r02_ncu_summary.txt')):
+            if line.startswith('kernel:'):
+                on = kernel in line
+            elif on and ('dram__bytes_read.sum' in line or 'dram__bytes_write.sum' in line):
+                f = line.split()
+                scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}.get(f[2] if len(f) > 2 else 'byte', 1.0)
+                tot += float(f[1]) * scale
+        return tot or None
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -458,7 +475,7 @@ def measure(args, rank, world, dist):
         g1 = stages.get('k_gemm1')
         if g1:     # the dominant kernel: stage 1 of DF-K
             roof = {'bound': 'tensor', 'achieved': g1['achieved'], 'peak': tensor_peak, 'unit': 'TOP/s (int8)', 'frac': g1['frac'],
-                    'traffic': None,
+                    'traffic': ncu_traffic('i8gemm_ar_kernel') if args.workload == 'c60-def2svp-df' and world == 1 else None,
                     'kernel': 'i8gemm_ar_kernel (tcgen05.mma.kind::i8, stage 1 of DF-K: Y = (P|mu nu) C~), CUDA events around '
                               'each of its launches inside the timed steps',
                     'ms_per_launch': g1['ms_per_launch'], 'launches_per_step': g1['launches_per_step'],

@@ -31,12 +31,13 @@ for path in sys.argv[1:]:
     rows = list(csv.reader(open(path)))
     hdr = rows[0]
     print('==', path)
+    units = dict(zip(hdr, rows[1])) if len(rows) > 1 else {}
     for r in rows[2:]:
         d = dict(zip(hdr, r))
         print('kernel:', d.get('Kernel Name', '')[:110])
         for k in KEYS:
             if k in d and d[k] != '':
-                print('   %-85s %s' % (k, d[k]))
+                print('   %-85s %s %s' % (k, d[k], units.get(k, '')))
         extra = [k for k in hdr if 'stalled' in k and 'per_issue_active' in k and k not in KEYS]
         for k in extra:
             try:
