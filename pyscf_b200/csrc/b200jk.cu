@@ -61,7 +61,15 @@ extern "C" int b200jk_create2(b200jk_handle* out, const int32_t* atm, int natm, 
         CK(cudaEventCreate(&h->ev1));
         CK(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
         h->side.resize(8); h->side_ev.resize(8);
-        for (auto& s : h->side) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        {
+            // B200JK_LAUNCH_ORDER=1 (tuning experiment): the second half of the side streams gets the highest priority; the cheap,
+            // latency-bound classes are launched there FIRST so that they run under the big classes instead of alone at the end
+            int lo = 0, hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            const bool pri = getenv("B200JK_LAUNCH_ORDER") && atoi(getenv("B200JK_LAUNCH_ORDER")) == 1;
+            for (size_t i = 0; i < h->side.size(); i++)
+                CK(cudaStreamCreateWithPriority(&h->side[i], cudaStreamNonBlocking, (pri && i >= h->side.size() / 2) ? hi : lo));
+        }
         for (auto& e : h->side_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 #endif
         (void)natm; (void)nenv;
@@ -399,8 +407,25 @@ static int direct_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, 
         CK(cudaEventRecord(h->ev_in, st));
         for (auto& s : h->side) CK(cudaStreamWaitEvent(s, h->ev_in, 0));
 #endif
+        // launch order and stream of every job: by default descending cost, round-robin over the side streams
+        std::vector<size_t> order(jobs.size());
+        std::vector<int> job_stream(jobs.size());
+        for (size_t i = 0; i < jobs.size(); i++) { order[i] = i; job_stream[i] = (int)(i % 8); }
+        {
+            static const int launch_order = getenv("B200JK_LAUNCH_ORDER") ? atoi(getenv("B200JK_LAUNCH_ORDER")) : 0;
+            if (launch_order == 1 && jobs.size() > 8) {
+                double total = 0, cum = 0;
+                for (const Job& jb : jobs) total += jb.cost;
+                size_t first_small = jobs.size();
+                for (size_t i = jobs.size(); i-- > 0;) { if (cum + jobs[i].cost > 0.25 * total) break; cum += jobs[i].cost; first_small = i; }
+                size_t n = 0;
+                for (size_t i = first_small; i < jobs.size(); i++) { order[n] = i; job_stream[i] = 4 + (int)((i - first_small) % 4); n++; }   // small ones first, high-priority streams
+                for (size_t i = 0; i < first_small; i++) { order[n] = i; job_stream[i] = (int)(i % 4); n++; }
+            }
+        }
         int jn = 0;
-        for (size_t ji = 0; ji < jobs.size(); ji++) {
+        for (size_t oi = 0; oi < jobs.size(); oi++) {
+            const size_t ji = order[oi];
             const Job& jb = jobs[ji];
             int cb = jb.cb, ck = jb.ck;
             if (owner[ji] >= 0) {                       // a class given whole to one rank
@@ -424,7 +449,7 @@ static int direct_jk_impl(b200jk_handle h, const double* dm, int n_dm, int nao, 
             P.bra_nprim_max = B.kept[0].nprim;  // lists are sorted by primitive count, largest first
             P.ket_nprim_max = K.kept[0].nprim;
 #ifndef B200JK_EMULATE
-            cudaStream_t ss = h->profile ? st : h->side[jn % h->side.size()];
+            cudaStream_t ss = h->profile ? st : h->side[job_stream[ji] % h->side.size()];
             if (h->profile) {
                 if (h->cls_ev.empty()) { h->cls_ev.resize(2 * NPC * NPC); for (auto& e : h->cls_ev) CK(cudaEventCreate(&e)); }
                 CK(cudaEventRecord(h->cls_ev[2 * (cb * NPC + ck)], ss));

@@ -35,6 +35,7 @@ struct KParams {
     int kchunk;
     int bra_nprim_max, ket_nprim_max;
     int shard_rank, shard_world;   // multi-GPU: this rank owns bra pairs bx = i*world + rank (lists are cost-sorted)
+    int pslice;                    // thread-per-quartet kernels: bra primitive pairs per CTA slice (blockIdx.z)
     unsigned long long* counters;  // [0] quartets computed, [1] quartets screened out (may be null)
 };
 
@@ -407,34 +408,47 @@ void jk_block(const KParams& P, int bx, int by, BlockSmem<C>& sm)
     bulk_wait(&sm.mbar_bra, 0);
 #endif
 
-    // ---- on-device screening: compact the surviving kets of this chunk
-    B2_ALL_THREADS(tid)
-        for (int kk = kbeg + tid; kk < kend; kk += GC::NT) {
-            const ShellPair& kp = P.ket_pairs[kk];
-            bool keep = keep_quartet(bpair.q, kp.q, bpair.ish, bpair.jsh, kp.ish, kp.jsh, P.dmc, P.nsh, P.tol,
-                                     P.vj != nullptr, P.vk != nullptr);
-            if (keep) {
-#if defined(__CUDA_ARCH__)
-                int pos = atomicAdd(&sm.nk, 1);
-#else
-                int pos = sm.nk++;
-#endif
-                sm.klist[pos] = kk;
-            }
+    // The CTA's ket range may be longer than the shared list: it is walked in sub-chunks of KCH_MAX kets (screen, compact,
+    // process), the stationary J[ij] block staying in registers across all of them.  Fewer, longer CTAs measured faster
+    // (profiles/r02_ab_direct_host_knobs.txt: the per-CTA prologue and the drain of the last batches are not free).
+    for (int sub = kbeg; sub < kend; sub += KCH_MAX) {
+        const int send = (sub + KCH_MAX < kend) ? sub + KCH_MAX : kend;
+        if (sub > kbeg) {
+            B2_SYNC();      // every group has left group_proc: the list and the batch counter can be reset
+            B2_ALL_THREADS(tid)
+                if (tid == 0) { sm.nk = 0; sm.next = 0; }
+            B2_END
+            B2_SYNC();
         }
-    B2_END
-    B2_SYNC();
-    const int nk = sm.nk;
+        // ---- on-device screening: compact the surviving kets of this sub-chunk
+        B2_ALL_THREADS(tid)
+            for (int kk = sub + tid; kk < send; kk += GC::NT) {
+                const ShellPair& kp = P.ket_pairs[kk];
+                bool keep = keep_quartet(bpair.q, kp.q, bpair.ish, bpair.jsh, kp.ish, kp.jsh, P.dmc, P.nsh, P.tol,
+                                         P.vj != nullptr, P.vk != nullptr);
+                if (keep) {
 #if defined(__CUDA_ARCH__)
-    if (P.counters && threadIdx.x == 0) {
-        atomicAdd(&P.counters[0], (unsigned long long)nk);
-        atomicAdd(&P.counters[1], (unsigned long long)(kend - kbeg - nk));
-    }
-    group_proc<C, SR>(P, sm, threadIdx.x / GC::TG, nk, bx, ctx);
+                    int pos = atomicAdd(&sm.nk, 1);
 #else
-    if (P.counters) { P.counters[0] += nk; P.counters[1] += kend - kbeg - nk; }
-    for (int grp = 0; grp < GC::NG; grp++) group_proc<C, SR>(P, sm, grp, nk, bx, ctxs);
+                    int pos = sm.nk++;
 #endif
+                    sm.klist[pos] = kk;
+                }
+            }
+        B2_END
+        B2_SYNC();
+        const int nk = sm.nk;
+#if defined(__CUDA_ARCH__)
+        if (P.counters && threadIdx.x == 0) {
+            atomicAdd(&P.counters[0], (unsigned long long)nk);
+            atomicAdd(&P.counters[1], (unsigned long long)(send - sub - nk));
+        }
+        group_proc<C, SR>(P, sm, threadIdx.x / GC::TG, nk, bx, ctx);
+#else
+        if (P.counters) { P.counters[0] += nk; P.counters[1] += send - sub - nk; }
+        for (int grp = 0; grp < GC::NG; grp++) group_proc<C, SR>(P, sm, grp, nk, bx, ctxs);
+#endif
+    }
 
     // ---- flush the register-resident J[ij] of the stationary bra pair
     if (P.vj && P.n_dm_j == 1) {

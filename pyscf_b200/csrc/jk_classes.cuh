@@ -1,6 +1,7 @@
 // jk_classes.cuh — instantiation and dispatch of the per-class direct J/K kernels.
 // One kernel per angular-momentum class (bra pair class >= ket pair class), 55 classes for s..f.
 #pragma once
+#include <cstdlib>
 #include <stdexcept>
 #include "jk_tpq.cuh"
 
@@ -14,7 +15,8 @@ constexpr int lane_eff_permille(int g) { return g <= 32 ? (32 / g) * g * 1000 / 
 #define B2_NVMAX 30        // largest register block (doubles) of ERI accumulators per thread
 #endif
 #ifndef B2_WANT_CTAS
-#define B2_WANT_CTAS 8     // CTAs per SM a class launch aims for when it sizes the ket chunks
+#define B2_WANT_CTAS 2     // CTAs per SM a class launch aims for when it sizes the ket chunks (measured on B200, benzene/cc-pVTZ:
+                           // 64: 22.6 ms, 32: 21.5, 16: 19.8, 8: 18.4, 4: 17.6, 3: 17.4, 2: 17.2, 1: 17.4; B200JK_WANT_CTAS overrides at run time)
 #endif
 #ifndef B2_PBMAX
 #define B2_PBMAX 1         // largest primitive batch (QClass::PB) of the block kernels; 1 = one primitive quartet per round
@@ -53,12 +55,21 @@ constexpr int choose_pb(int g, int nr, int h_bytes, int nslot)
 // the class fills the 148 SMs several times over
 inline int pick_kchunk(int nbra, int nket, int unit, int cap)
 {
-    long want_ctas = 148L * B2_WANT_CTAS;
+    static const long want_env = getenv("B200JK_WANT_CTAS") ? atol(getenv("B200JK_WANT_CTAS")) : 0;   // tuning experiment
+    long want_ctas = 148L * (want_env > 0 ? want_env : B2_WANT_CTAS);
     long ny = (want_ctas + nbra - 1) / nbra;
     long kc = (nket + ny - 1) / ny;
     if (kc < unit) kc = unit;
     if (kc > cap) kc = cap;
     return (int)kc;
+}
+
+// upper bound of the kets one CTA takes: by default unbounded (the block kernels walk their range in sub-chunks of KCH_MAX, the
+// thread-per-quartet kernels keep no list); B200JK_KETS_CAP=1 restores the round-1 cap (one list / 512 kets per CTA)
+inline int kets_cap(int round1_cap)
+{
+    static const bool old_cap = getenv("B200JK_KETS_CAP") && atoi(getenv("B200JK_KETS_CAP")) == 1;
+    return old_cap ? round1_cap : (1 << 30);
 }
 
 template <int LI, int LJ, int LK, int LL>
@@ -138,7 +149,8 @@ void launch_block_kernel(const KParams& P, dim3 grid, int nt, size_t smem, b2_st
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
         // leave half of the 228 KB for L1 (Rys tables, density blocks); the other half lets several CTAs co-reside
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, B2_CARVEOUT);
+        static const int carve_env = getenv("B200JK_CARVEOUT") ? atoi(getenv("B200JK_CARVEOUT")) : -1;   // tuning experiment
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve_env >= 0 ? carve_env : B2_CARVEOUT);
         configured = true;
     }
     kern<<<grid, nt, smem, st>>>(P);
@@ -154,11 +166,15 @@ void launch_one(KParams P, b2_stream_t st)
     using C = typename Cfg::C;
     if constexpr (TpqCfg<C>::eligible) {
         // low angular momentum: one thread per quartet, registers only (jk_tpq.cuh)
+        {
+            static const int ps_env = getenv("B200JK_TPQ_PSLICE") ? atoi(getenv("B200JK_TPQ_PSLICE")) : 0;   // tuning experiment
+            P.pslice = ps_env > 0 ? ps_env : TpqCfg<C>::PSLICE;
+        }
         const int nbx = (P.nbra + P.shard_world - 1) / P.shard_world;   // bra pairs of this rank
-        P.kchunk = pick_kchunk(nbx, P.nket, TpqCfg<C>::NT, TpqCfg<C>::KCHUNK);
+        P.kchunk = pick_kchunk(nbx, P.nket, TpqCfg<C>::NT, kets_cap(TpqCfg<C>::KCHUNK));
         int ny = (P.nket + P.kchunk - 1) / P.kchunk;
 #ifndef B200JK_EMULATE
-        dim3 grid(nbx, ny, (P.bra_nprim_max + TpqCfg<C>::PSLICE - 1) / TpqCfg<C>::PSLICE);
+        dim3 grid(nbx, ny, (P.bra_nprim_max + P.pslice - 1) / P.pslice);
         if (P.omega < 0.0) jk_tpq_kernel<C, true><<<grid, TpqCfg<C>::NT, 0, st>>>(P);   // erfc operator: two root sets
         else jk_tpq_kernel<C, false><<<grid, TpqCfg<C>::NT, 0, st>>>(P);
         cudaError_t e = cudaGetLastError();
@@ -167,7 +183,7 @@ void launch_one(KParams P, b2_stream_t st)
         (void)st;
         for (int bx = P.shard_rank; bx < P.nbra; bx += P.shard_world)
             for (int by = 0; by < ny; by++)
-                for (int bz = 0; bz * TpqCfg<C>::PSLICE < P.bra_nprim_max; bz++) {
+                for (int bz = 0; bz * P.pslice < P.bra_nprim_max; bz++) {
                     if (P.omega < 0.0) tpq_block<C, true>(P, bx, by, bz);
                     else tpq_block<C, false>(P, bx, by, bz);
                 }
@@ -175,7 +191,7 @@ void launch_one(KParams P, b2_stream_t st)
         return;
     }
     const int nbx = (P.nbra + P.shard_world - 1) / P.shard_world;
-    P.kchunk = pick_kchunk(nbx, P.nket, Cfg::GC::NSLOT, KCH_MAX);
+    P.kchunk = pick_kchunk(nbx, P.nket, Cfg::GC::NSLOT, kets_cap(KCH_MAX));
     int ny = (P.nket + P.kchunk - 1) / P.kchunk;
 #ifndef B200JK_EMULATE
     size_t smem = sizeof(BlockSmem<C>);

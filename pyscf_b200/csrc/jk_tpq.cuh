@@ -286,8 +286,8 @@ void tpq_block(const KParams& P, int bx, int by, int bz)
     const int kbeg = by * P.kchunk;
     const int kend = (kbeg + P.kchunk < kmax) ? kbeg + P.kchunk : kmax;
     if (kbeg >= kend) return;
-    const int ib0 = bz * T::PSLICE;
-    const int ib1 = (ib0 + T::PSLICE < bpair.nprim) ? ib0 + T::PSLICE : bpair.nprim;
+    const int ib0 = bz * P.pslice;
+    const int ib1 = (ib0 + P.pslice < bpair.nprim) ? ib0 + P.pslice : bpair.nprim;
     if (ib0 >= ib1) return;
 #if defined(__CUDA_ARCH__)
     {

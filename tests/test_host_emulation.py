@@ -359,3 +359,31 @@ def test_patch_cache_follows_the_molecule(emu_lib):
     assert mf.nreset == 1 and not mf._b200_opts._d
     # the module-level cache is bounded and keyed on live objects
     JK._opt_cache.clear()
+
+
+def test_long_ket_ranges_walk_sub_chunks(emu_lib):
+    """A CTA whose ket range is longer than the shared ket list (KCH_MAX = 512) walks it in sub-chunks with the stationary J[ij]
+    block kept in registers: forced here with one CTA per bra pair (B200JK_WANT_CTAS=1, read once per process, hence the
+    subprocess) on (Gly)4/STO-3G, whose 1176 (ss| pairs need three sub-chunks; hermi 1 and a stack of non-symmetric densities."""
+    import subprocess, sys, os, textwrap
+    code = textwrap.dedent('''
+        import os, sys, numpy as np
+        sys.path.insert(0, %r)
+        from pyscf_b200 import gto
+        from pyscf_b200.gto.mole import geometry
+        from pyscf_b200.jk import VHFOpt
+        from oracle import oracle as O
+        mol = gto.M(atom=geometry('gly4'), basis='sto-3g')
+        nao = mol.nao
+        np.random.seed(2)
+        dm = np.random.random((nao, nao)) * 0.1
+        opt = VHFOpt(mol, libpath=%r)
+        for d, hermi in ((dm + dm.T, 1), (np.array([dm, dm.T * 0.5]), 0)):
+            vj, vk = opt.get_jk(d, hermi=hermi)
+            rj, rk = O.get_jk(mol, d)
+            assert abs(vj - rj).max() < 1e-10 and abs(vk - rk).max() < 1e-10
+        print('OK')
+    ''') % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), emu_lib)
+    env = dict(os.environ, B200JK_WANT_CTAS='1')
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and 'OK' in out.stdout, out.stderr[-2000:]

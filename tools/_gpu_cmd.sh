@@ -1,4 +1,9 @@
 cd "${GRAFT_REPO_ROOT}"; mkdir -p gpurun_out
-echo "== df tests"; timeout 1400 python -m pytest tests -m gpu -x -q -k "test_df or i8gemm" 2>&1 | tail -12
-echo "== c60"; timeout 600 python bench.py --workload c60-def2svp-df --steps 5 --warmup 3 --no-cpu > gpurun_out/r02q_c60.json 2> gpurun_out/r02q_c60.err; tail -c 300 gpurun_out/r02q_c60.err; python tools/bench_brief.py gpurun_out/r02q_c60.json | cut -c1-900
-echo "== taxol"; timeout 600 python bench.py --workload taxol-def2tzvp-df --steps 4 --warmup 3 --no-cpu > gpurun_out/r02q_taxol.json 2> gpurun_out/r02q_taxol.err; python tools/bench_brief.py gpurun_out/r02q_taxol.json | cut -c1-900
+echo "== direct tests"; timeout 900 python -m pytest tests -m gpu -x -q -k "direct or short_range or edge or screening or cart or grad or incore" 2>&1 | tail -3
+run() { tag=$1; shift; echo "== $tag"; env "$@" timeout 300 python bench.py --steps 20 --warmup 5 --no-df --no-cpu > gpurun_out/r02v_$tag.json 2> gpurun_out/r02v_$tag.err; python tools/bench_brief.py gpurun_out/r02v_$tag.json | cut -c1-100; }
+run default X=1
+run cap512 B200JK_KETS_CAP=1
+run pslice16 B200JK_TPQ_PSLICE=16
+run pslice4 B200JK_TPQ_PSLICE=4
+run want1 B200JK_WANT_CTAS=1
+run want3 B200JK_WANT_CTAS=3
