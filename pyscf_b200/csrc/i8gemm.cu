@@ -263,6 +263,8 @@ void gemm_ar_acc(const SliceStack& A, const SliceStack& B, double* C, long ldc, 
         if (eff > best_eff + 1e-9) { best_eff = eff; best = kse; }
         if (items > 12L * nsm) break;
     }
+    static const int ks_env = getenv("B200JK_G2_KS") ? atoi(getenv("B200JK_G2_KS")) : 0;   // tuning experiment: force the K-range count
+    if (ks_env > 0) best = std::min(ks_env, std::max(1, nkb));
     P.ar_kb_per = (nkb + best - 1) / best;
     P.ar_ksplit = (nkb + P.ar_kb_per - 1) / P.ar_kb_per;
     P.ar_ntiles = tiles;
