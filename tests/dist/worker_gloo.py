@@ -30,6 +30,23 @@ assert abs(vj - rj).max() < 1e-10 and abs(vk - rk).max() < 1e-10, (abs(vj - rj).
 # partial results really are partial (each rank did only part of the work)
 pj, pk = sj.engine.get_jk(dm, hermi=1)
 assert abs(pj - rj).max() > 1e-3
+# the partition on a cost table handed in by the host layer (b200jk_set_class_costs; on GPUs the table is measured by
+# parallel.calibrate_partition): with trusted costs every class goes WHOLE to one rank, and the sum must not change
+import ctypes
+from pyscf_b200 import lib as _lib
+h = sj.h
+table = np.zeros(100)
+for cb in range(10):
+    for ck in range(cb + 1):
+        table[cb * 10 + ck] = 0.05 + 0.01 * ((7 * cb + 3 * ck) % 11)     # any positive table, the same on both ranks
+h.check(h.lib.b200jk_set_class_costs(h._h, _lib.dptr(table), 100), 'b200jk_set_class_costs')
+vj2, vk2 = sj.get_jk(dm, hermi=1)
+assert abs(vj2 - rj).max() < 1e-10 and abs(vk2 - rk).max() < 1e-10
+pj2, pk2 = sj.engine.get_jk(dm, hermi=1)
+assert abs(pj2 - pj).max() > 1e-6          # a different split of the work than the model-based one
+vk3 = sj.get_jk(dm, hermi=1, with_j=False)[1]     # K alone: one output allocated / reduced
+assert abs(vk3 - rk).max() < 1e-10
+h.check(h.lib.b200jk_set_class_costs(h._h, None, 0), 'b200jk_set_class_costs')
 # DF path
 dfobj = DF(mol, 'weigend', libpath=emu).build()
 sd = ShardedJK(dfobj)
