@@ -35,3 +35,21 @@ def test_reference_arm_json_line():
 def test_reference_arm_other_ranks_idle():
     p = _run({'RANK': '1', 'WORLD_SIZE': '2', 'LOCAL_RANK': '1'})
     assert p.returncode == 0 and p.stdout.strip() == ''
+
+
+def test_df_records_have_their_parity_fixtures_and_traffic_source():
+    """Every DF configuration the bench appends to its line has its at-size oracle fixture committed, and the roofline traffic of
+    the C60 record can be read from the committed ncu summary."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import bench
+    import df_size_check as S
+    for name, *_ in bench.DF_EXTRAS:
+        fixtures = bench.SIZE_FIXTURE[name]
+        for f in fixtures:
+            if f is not None:
+                z = S.load(f)
+                assert z is not None, f
+                assert int(z['nocc']) == bench.WORKLOADS[name]['nocc']
+    t = bench.ncu_traffic('i8gemm_ar_kernel')
+    assert t is not None and 1e9 < t < 1e10
